@@ -1,0 +1,97 @@
+/* specfab_b200 -- C ABI of the B200-native batched fabric-evolution engine.
+ *
+ * Drop-in boundary for the hot path of nicholasmr/specfab.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference tree).
+ * Plain C: pointers + sizes, no C++/torch types.  Error handling: every function returns
+ * SFB_OK (0) or a negative SFB_E* code; sfb_last_error() gives the message.  (The reference
+ * `stop`s the process instead: src/homogenizations.f90:95,112,183,220; src/frames.f90:48.)
+ *
+ * Array convention (same as f2py hands to Fortran): batched arguments are the
+ * reference's own arrays with a LEADING node dimension in Fortran column-major order, i.e. the
+ * node index is the contiguous one:
+ *     nlm(N, nlm_len) complex(8)  ->  double[2*ld*nlm_len], element (node p, coef j) at 2*(j*ld+p)
+ *     ugrad(N,3,3), tau(N,3,3)    ->  double[9*ld],         element (p,i,k) at (i+3k)*ld + p
+ *     Eij(N,6), lami(N,3), ei(N,3,3) [ei(p,i,:) = i-th eigenvector], a2(N,3,3), a4(N,3,3,3,3)
+ * `ld` (leading dimension, >= N) is given per call.
+ *
+ * Pointer spaces: functions ending in `_dev` take DEVICE pointers and a cudaStream_t (passed as
+ * void*, may be NULL) and are asynchronous; the others take HOST pointers, stage through device
+ * memory on the current CUDA device and return when the result is in the output buffers.
+ * There is no CPU fallback: without a usable CUDA device every call returns SFB_ECUDA.
+ */
+#ifndef SPECFAB_B200_H
+#define SPECFAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    SFB_OK = 0,
+    SFB_EINVAL = -1,   /* bad argument (odd L, L<4, L>20, null pointer, ld<N ...) */
+    SFB_ENOINIT = -2,  /* sfb_init() not called */
+    SFB_ECUDA = -3,    /* CUDA runtime error / no device */
+    SFB_ENOTBUILT = -4 /* kernel for this L was not compiled into the library */
+};
+
+/* term mask of the fused step (src/specfabpy/integrator.py:55-77) */
+enum { SFB_LROT = 1, SFB_DDRX = 2, SFB_CDRX = 4, SFB_REG = 8 };
+/* time integrators: Euler = src/dynamics.f90:108 ; RK4 = classical, BASELINE config 2 */
+enum { SFB_EULER = 1, SFB_RK4 = 4 };
+
+/* per-node status flags written by the Eij routines (0 = ok) */
+enum { SFB_ST_TAYLOR_FALLBACK = 1, SFB_ST_TAYLOR_FAILED = 2, SFB_ST_NONFINITE = 4 };
+
+/* init(L) -> lm(2,nlm_len), nlm_len        src/specfabpy.f90:150-160, src/specfab.f90:37-53
+ * Loads tables, fixes L for subsequent calls (module state in the reference).  Idempotent. */
+int sfb_init(int L);
+int sfb_nlm_len(void);                 /* src/specfabpy.f90:162-166 */
+int sfb_get_lm(int32_t* lm /* [2*nlm_len], lm(1,j)=l, lm(2,j)=m */);
+void sfb_finalize(void);
+const char* sfb_last_error(void);
+/* library/build information: JSON string (compiled L list, tile shapes, DFMA counts) */
+const char* sfb_build_info(void);
+
+typedef struct sfb_step_opts {
+    double dt;
+    double iota;        /* M_LROT eps^1 coefficient       src/dynamics.f90:52 */
+    double zeta;        /* M_LROT eps^2 coefficient */
+    double nu_mult;     /* multiplier on M_REG (1 = calibrated regularisation) */
+    double gamma0;      /* DDRX rate factor (caller-multiplied in the reference, src/dynamics.f90:260) */
+    double lambda;      /* CDRX rate factor (src/dynamics.f90:483) */
+    const double* gamma0_arr; /* optional per-node rate factors [N] (same pointer space as the call), or NULL */
+    const double* lambda_arr;
+    int32_t terms;      /* SFB_LROT | SFB_DDRX | SFB_CDRX | SFB_REG */
+    int32_t scheme;     /* SFB_EULER | SFB_RK4 */
+    int32_t nsteps;     /* number of consecutive steps with the same forcing (>= 1) */
+    int32_t reserved;
+} sfb_step_opts;
+
+/* Fused batched time step:  nlm <- nlm + dt * (M_LROT + gamma0*M_DDRX + lambda*M_CDRX + M_REG) nlm
+ * Replaces the per-node loop  M = sf.M_LROT(..) + sf.M_REG(..) + ..; nlm + dt*matmul(M,nlm)
+ * (src/specfabpy/integrator.py:73-77, src/dynamics.f90:99-110, src/specfabpy/fenics/CPO.py:200-202).
+ * D, W are the symmetric / antisymmetric parts of ugrad; tau may be NULL (then tau := D, as
+ * src/specfabpy/integrator.py:39).  nlm_in may equal nlm_out (in-place). */
+int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
+                 const double* ugrad, const double* tau, const sfb_step_opts* opts);
+int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                     const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
+                     const sfb_step_opts* opts, void* stream);
+
+/* simple device-memory helpers so that FFI callers need no CUDA binding of their own */
+int sfb_dev_malloc(void** p, int64_t bytes);
+int sfb_dev_free(void* p);
+int sfb_memcpy_h2d(void* dst, const void* src, int64_t bytes);
+int sfb_memcpy_d2h(void* dst, const void* src, int64_t bytes);
+int sfb_host_alloc_pinned(void** p, int64_t bytes);
+int sfb_host_free_pinned(void* p);
+int sfb_sync(void);
+int sfb_device_count(void);
+int sfb_set_device(int dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,144 @@
+"""Build libspecfab_b200.so (sm_100a) in-tree:  python -m specfab_b200.build [-j N] [--L 8,12]
+
+1. generate the straight-line operator-apply code for every (L, term set)  (codegen/emit_step.py)
+2. nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo each translation unit (parallel)
+3. link specfab_b200/libspecfab_b200.so  (C ABI declared in include/specfab_b200.h)
+
+nvcc cross-compiles without a GPU.  Generated sources go to specfab_b200/csrc/gen (git-ignored).
+"""
+import argparse
+import concurrent.futures as cf
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+GEN = os.path.join(CSRC, "gen")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libspecfab_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-I", CSRC,
+          "-I", os.path.join(HERE, "..", "include")]
+
+ALL_L = [4, 6, 8, 10, 12, 14, 16, 18, 20]
+
+# tuning table: (L, ddrx) -> (roles R, tile nodes TN, min CTAs/SM for __launch_bounds__)
+TUNE = {
+    (4, 0): (1, 32, 2), (4, 1): (1, 32, 2),
+    (6, 0): (1, 32, 2), (6, 1): (2, 32, 2),
+    (8, 0): (2, 32, 2), (8, 1): (2, 32, 2),
+    (10, 0): (2, 32, 2), (10, 1): (2, 32, 2),
+    (12, 0): (2, 32, 2), (12, 1): (2, 32, 2),
+    (14, 0): (2, 16, 2), (14, 1): (4, 16, 2),
+    (16, 0): (4, 16, 2), (16, 1): (4, 16, 2),
+    (18, 0): (4, 16, 2), (18, 1): (4, 16, 2),
+    (20, 0): (4, 16, 2), (20, 1): (4, 16, 2),
+}
+
+
+def _write_if_changed(path, text):
+    if os.path.exists(path) and open(path).read() == text:
+        return False
+    with open(path, "w") as f:
+        f.write(text)
+    return True
+
+
+def generate(Ls):
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from specfab_b200.codegen import emit_step, emit_tables
+    os.makedirs(GEN, exist_ok=True)
+    units, metas = [], []
+    for L in Ls:
+        for dd in (0, 1):
+            R, TN, MINB = TUNE[(L, dd)]
+            tag = "L%d_%s" % (L, "ddrx" if dd else "lrot")
+            body, meta = emit_step.emit(L, dd, R, TN)
+            _write_if_changed(os.path.join(GEN, "apply_%s.inc" % tag), body)
+            cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_R %d\n#define SFB_TN %d\n#define SFB_MINB %d\n'
+                  '#define SFB_NAME sfb_launch_step_%s\n#define SFB_APPLY_INC "gen/apply_%s.inc"\n'
+                  '#include "sfb_step_kernel.cuh"\n' % (L, dd, R, TN, MINB, tag, tag))
+            path = os.path.join(GEN, "step_%s.cu" % tag)
+            _write_if_changed(path, cu)
+            units.append(path)
+            meta["tag"] = tag
+            metas.append(meta)
+    reg = ["// GENERATED registry of step launchers"]
+    for m in metas:
+        reg.append('extern "C" cudaError_t sfb_launch_step_%s(const SfbStepParams&, const SfbRegConst&, cudaStream_t);' % m["tag"])
+    reg.append("static const SfbStepEntry kStepRegistry[] = {")
+    for m in metas:
+        reg.append("  {%d, %d, %d, %d, %d, sfb_launch_step_%s}," % (m["L"], m["ddrx"], m["R"], m["TN"], m["dfma_node"], m["tag"]))
+    reg.append("};")
+    _write_if_changed(os.path.join(GEN, "registry.inc"), "\n".join(reg) + "\n")
+    _write_if_changed(os.path.join(GEN, "tables.inc"), emit_tables.emit())
+    with open(os.path.join(GEN, "meta.json"), "w") as f:
+        json.dump(metas, f, indent=1)
+    return units, metas
+
+
+def _deps_hash(src):
+    h = hashlib.sha1()
+    files = [src] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    files += [os.path.join(HERE, "..", "include", "specfab_b200.h")]
+    if "step_" in os.path.basename(src):
+        tag = os.path.basename(src)[5:-3]
+        files.append(os.path.join(GEN, "apply_%s.inc" % tag))
+    else:
+        files += [os.path.join(GEN, "registry.inc"), os.path.join(GEN, "tables.inc")]
+    for f in files:
+        h.update(open(f, "rb").read())
+    h.update(" ".join(CFLAGS + ARCH).encode())
+    return h.hexdigest()
+
+
+def compile_one(src, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    stamp = obj + ".sha1"
+    hsh = _deps_hash(src)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hsh:
+        return obj, 0.0, ""
+    t0 = time.time()
+    cmd = [NVCC] + ARCH + CFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, p.stdout, p.stderr))
+    with open(stamp, "w") as f:
+        f.write(hsh)
+    return obj, time.time() - t0, p.stderr
+
+
+def build(Ls=None, jobs=None, verbose=False):
+    Ls = Ls or ALL_L
+    jobs = jobs or max(1, (os.cpu_count() or 2))
+    units, metas = generate(Ls)
+    units = units + [os.path.join(CSRC, "sfb_api.cu")]
+    objs = []
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        for obj, dt, log in ex.map(lambda s: compile_one(s, verbose), units):
+            objs.append(obj)
+            if dt:
+                print("  compiled %-28s %6.1fs" % (os.path.basename(obj), dt), flush=True)
+            if verbose and log:
+                print(log)
+    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))
+    print("linked", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-j", type=int, default=None)
+    ap.add_argument("--L", type=str, default=None, help="comma list of truncations to build (default: all even 4..20)")
+    ap.add_argument("-v", action="store_true")
+    a = ap.parse_args()
+    build([int(x) for x in a.L.split(",")] if a.L else None, a.j, a.v)

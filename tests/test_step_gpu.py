@@ -1,0 +1,191 @@
+"""GPU parity of the fused step kernels against the CPU oracle, through the C ABI.
+Tolerances (BASELINE.json north_star): relative 1e-12 per step, 1e-9 after 1000 steps (FP64)."""
+import numpy as np
+import pytest
+
+import specfab_oracle as orc
+from util import random_states, random_ugrad, random_tau, relerr_nodes
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-12
+TOL_1000 = 1e-9
+
+
+def oracle_steps(L, x, ug, tau, scheme, nsteps, **kw):
+    orc.init(L)
+    out = np.array(x, dtype=np.complex128)
+    stepf = orc.step_rk4 if scheme == "rk4" else orc.step_euler
+    dt = kw.pop("dt")
+    for p in range(out.shape[0]):
+        v = out[p]
+        kwp = dict(kw)
+        for key in ("Gamma0", "Lambda"):
+            if np.ndim(kwp.get(key, 0.0)):
+                kwp[key] = kwp[key][p]
+        for _ in range(nsteps):
+            v = stepf(v, dt, ug[p], None if tau is None else tau[p], **kwp)
+        out[p] = v
+    return out
+
+
+def built_L():
+    import specfab_b200 as sf
+    return sorted({k["L"] for k in sf.build_info()["step_kernels"]})
+
+
+@pytest.mark.parametrize("L", [4, 6, 8, 12, 20])
+@pytest.mark.parametrize("scheme", ["euler", "rk4"])
+@pytest.mark.parametrize("physical", [True, False])
+def test_step_lrot_reg(L, scheme, physical):
+    import specfab_b200 as sf
+    if L not in built_L():
+        pytest.skip("L=%d not built" % L)
+    N = 77 if L <= 12 else 21
+    sf.init(L)
+    x = random_states(L, N, 100 + L, physical)
+    ug = random_ugrad(N, 200 + L)
+    dt = 3.912e-3
+    got = sf.step_arr(x, ug, dt=dt, iota=1.0, zeta=0.0, nu=1.0, terms=("lrot", "reg"), scheme=scheme)
+    ref = oracle_steps(L, x, ug, None, scheme, 1, dt=dt, iota=1.0, zeta=0.0, nu_mult=1.0)
+    assert relerr_nodes(got, ref).max() < TOL_STEP
+
+
+@pytest.mark.parametrize("L", [4, 8, 12, 20])
+@pytest.mark.parametrize("scheme", ["euler", "rk4"])
+def test_step_all_terms(L, scheme):
+    import specfab_b200 as sf
+    if L not in built_L():
+        pytest.skip("L=%d not built" % L)
+    N = 45 if L <= 12 else 19
+    sf.init(L)
+    x = random_states(L, N, 300 + L, True)
+    ug = random_ugrad(N, 400 + L)
+    tau = random_tau(N, 500 + L)
+    dt = 3.912e-3
+    kw = dict(iota=0.8, zeta=0.3, Gamma0=4.0, Lambda=0.1)
+    got = sf.step_arr(x, ug, tau, dt=dt, nu=1.5, terms=("lrot", "ddrx", "cdrx", "reg"), scheme=scheme, **kw)
+    ref = oracle_steps(L, x, ug, tau, scheme, 1, dt=dt, nu_mult=1.5, use_ddrx=True, use_cdrx=True, **kw)
+    assert relerr_nodes(got, ref).max() < TOL_STEP
+
+
+def test_step_ddrx_tau_defaults_to_D_and_pernode_rates():
+    import specfab_b200 as sf
+    L, N = 8, 33
+    sf.init(L)
+    x = random_states(L, N, 7, False)
+    ug = random_ugrad(N, 8)
+    rng = np.random.default_rng(9)
+    G0 = rng.uniform(0.5, 5.0, N)
+    Lam = rng.uniform(0.0, 0.5, N)
+    D = (ug + ug.transpose(0, 2, 1)) / 2
+    dt = 2e-3
+    got = sf.step_arr(x, ug, None, dt=dt, Gamma0=G0, Lambda=Lam, terms=("lrot", "ddrx", "cdrx", "reg"))
+    ref = oracle_steps(L, x, ug, D, "euler", 1, dt=dt, Gamma0=G0, Lambda=Lam, use_ddrx=True, use_cdrx=True)
+    assert relerr_nodes(got, ref).max() < TOL_STEP
+
+
+def test_terms_can_be_switched_off():
+    import specfab_b200 as sf
+    L, N = 8, 20
+    sf.init(L)
+    x = random_states(L, N, 17, True)
+    ug = random_ugrad(N, 18)
+    tau = random_tau(N, 19)
+    dt = 1e-2
+    got = sf.step_arr(x, ug, tau, dt=dt, Gamma0=3.0, terms=("ddrx",))
+    ref = oracle_steps(L, x, ug, tau, "euler", 1, dt=dt, Gamma0=3.0, use_lrot=False, use_ddrx=True, use_reg=False)
+    assert relerr_nodes(got, ref).max() < TOL_STEP
+    got = sf.step_arr(x, ug, dt=dt, terms=("lrot",))
+    ref = oracle_steps(L, x, ug, None, "euler", 1, dt=dt, use_reg=False)
+    assert relerr_nodes(got, ref).max() < TOL_STEP
+
+
+def test_config1_parcel_1000_euler_steps():
+    """BASELINE config 1: L=8, LROT+REG, uniaxial compression, 1000 Euler steps from isotropy."""
+    import specfab_b200 as sf
+    L = 8
+    lm, n = sf.init(L)
+    N = 3
+    x = np.zeros((N, n), dtype=np.complex128)
+    x[:, 0] = 1 / np.sqrt(4 * np.pi)
+    ug = np.zeros((N, 3, 3))
+    ug[0] = np.diag([0.5, 0.5, -1.0])
+    ug[1] = np.array([[0.0, 0.0, 1.0], [0, 0, 0], [0, 0, 0]])          # simple shear
+    ug[2] = random_ugrad(1, 5)[0]
+    dt = -np.log(0.02) / 1000
+    got = sf.step_arr(x, ug, dt=dt, terms=("lrot", "reg"), nsteps=1000)
+    ref = oracle_steps(L, x, ug, None, "euler", 1000, dt=dt)
+    assert relerr_nodes(got, ref).max() < TOL_1000
+    orc.init(L)
+    a2 = orc.a2(got[0])
+    assert abs(np.trace(a2) - 1) < 1e-12 and a2[2, 2] > 0.8     # single maximum along z
+
+
+def test_1000_steps_all_terms_rk4():
+    import specfab_b200 as sf
+    L, N = 8, 4
+    sf.init(L)
+    x = random_states(L, N, 31, True, decay=0.3)
+    ug = random_ugrad(N, 32)
+    tau = random_tau(N, 33)
+    dt = 3.912e-3
+    kw = dict(Gamma0=4.0, Lambda=0.05)
+    got = sf.step_arr(x, ug, tau, dt=dt, terms=("lrot", "ddrx", "cdrx", "reg"), scheme="rk4", nsteps=250, **kw)
+    ref = oracle_steps(L, x, ug, tau, "rk4", 250, dt=dt, use_ddrx=True, use_cdrx=True, **kw)
+    assert relerr_nodes(got, ref).max() < TOL_1000
+
+
+def test_empty_and_ragged_and_errors():
+    import specfab_b200 as sf
+    L = 8
+    lm, n = sf.init(L)
+    assert n == 45 and lm.shape == (2, 45) and tuple(lm[:, 1]) == (2, -2)
+    out = sf.step_arr(np.zeros((0, n), complex), np.zeros((0, 3, 3)), dt=0.1)
+    assert out.shape == (0, n)
+    for N in (1, 15, 16, 17, 31, 32, 33, 100):
+        x = random_states(L, N, N, True)
+        ug = random_ugrad(N, N + 1)
+        got = sf.step_arr(x, ug, dt=1e-3)
+        ref = oracle_steps(L, x, ug, None, "euler", 1, dt=1e-3)
+        assert relerr_nodes(got, ref).max() < TOL_STEP
+    with pytest.raises(sf.SpecfabB200Error):
+        sf.init(7)
+    with pytest.raises(sf.SpecfabB200Error):
+        sf.init(22)
+    sf.init(L)
+    with pytest.raises(ValueError):
+        sf.step_arr(np.zeros((3, n - 1), complex), np.zeros((3, 3, 3)), dt=0.1)
+
+
+def test_eps_zero_gives_nan_like_reference():
+    """src/dynamics.f90:73: zeta/sqrt(tr eps^2) is 0/0 for eps == 0 -> NaN state (silent in the reference)."""
+    import specfab_b200 as sf
+    L = 8
+    sf.init(L)
+    x = random_states(L, 2, 3, True)
+    ug = np.zeros((2, 3, 3))
+    ug[1] = random_ugrad(1, 4)[0]
+    got = sf.step_arr(x, ug, dt=1e-3)
+    assert np.isnan(got[0]).any() and np.isfinite(got[1]).all()
+
+
+def test_large_field_linearity_property():
+    """Full-size property check (no oracle at this size): LROT+REG Euler is linear in nlm."""
+    import specfab_b200 as sf
+    L = 8
+    sf.init(L)
+    N = 200_000
+    rng = np.random.default_rng(1)
+    x1 = random_states(L, N, 41, True)
+    x2 = random_states(L, N, 42, False)
+    ug = random_ugrad(N, 43)
+    a, b = 0.7, -1.3
+    y1 = sf.step_arr(x1, ug, dt=5e-3, scheme="rk4")
+    y2 = sf.step_arr(x2, ug, dt=5e-3, scheme="rk4")
+    y12 = sf.step_arr(a * x1 + b * x2, ug, dt=5e-3, scheme="rk4")
+    assert relerr_nodes(y12, a * y1 + b * y2).max() < 1e-12
+    # spot-check 16 scattered nodes against the oracle
+    sel = rng.choice(N, 16, replace=False)
+    ref = oracle_steps(L, x1[sel], ug[sel], None, "rk4", 1, dt=5e-3)
+    assert relerr_nodes(y1[sel], ref).max() < TOL_STEP
