@@ -80,6 +80,39 @@ int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t l
                      const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
                      const sfb_step_opts* opts, void* stream);
 
+/* a2(nlm) -> (N,3,3)                         src/specfabpy.f90:583-590, src/moments.f90:37-44 */
+int sfb_a2_arr(const double* nlm, int64_t N, int64_t ld, double* a2);
+int sfb_a2_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a2, void* stream);
+/* a4(nlm) -> (N,3,3,3,3)                     src/specfabpy.f90:592-599, src/moments.f90:46-55.
+ * Reproduces the reference's real(4) constants and its ev(3,2,1,2) alias quirk (ev_c4__body.f90:78). */
+int sfb_a4_arr(const double* nlm, int64_t N, int64_t ld, double* a4);
+int sfb_a4_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a4, void* stream);
+/* eig(nlm) -> ei(N,3,3), lami(N,3): eigenframe of a2, largest eigenvalue first
+ *                                            src/specfabpy.f90:312-320, src/frames.f90:14-22.
+ * Eigenvector sign: largest |component| positive (LAPACK's choice is unpinned). */
+int sfb_eig_arr(const double* nlm, int64_t N, int64_t ld, double* ei, double* lami);
+int sfb_eig_arr_dev(const double* nlm, int64_t N, int64_t ld, double* ei, double* lami, void* stream);
+/* eigframe_arr(M(N,3,3), plane in {"ij","xy","xz"})   src/specfabpy.f90:333-344, src/frames.f90:24-60 */
+int sfb_eigframe_arr(const double* M, int64_t N, const char* plane, double* ei, double* lami);
+int sfb_eigframe_arr_dev(const double* M, int64_t N, int64_t ld, const char* plane, double* ei, double* lami, void* stream);
+/* Eij_tranisotropic_arr(nlm, e1,e2,e3 (N,3), Eij_grain(2), alpha, n_grain) -> Eij(N,6) = (E11,E22,E33,E23,E13,E12)
+ *                                            src/specfabpy.f90:474-486, src/enhancementfactors.f90:23-69.
+ * Only n_grain = 1.  status (optional, [N]) receives SFB_ST_* flags instead of the reference's `stop`
+ * (src/homogenizations.f90:183). */
+int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
+                              const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status);
+int sfb_Eij_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
+                                  const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status, void* stream);
+/* Fused a2 -> eigenframe -> Eij_tranisotropic in that frame (the eigenenhancements); batches
+ * src/specfabpy/fenics/enhancementfactor.py:101-128 / src/specfabpy/common.py:13-37.  ei/lami optional outputs. */
+int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                           double* Eij, double* ei, double* lami, int32_t* status);
+int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                               double* Eij, double* ei, double* lami, int32_t* status, void* stream);
+
+/* tuning knob: select an alternative compiled kernel variant (0 = default); unknown ids fall back to 0 */
+int sfb_set_variant(int variant);
+
 /* simple device-memory helpers so that FFI callers need no CUDA binding of their own */
 int sfb_dev_malloc(void** p, int64_t bytes);
 int sfb_dev_free(void* p);

@@ -399,7 +399,7 @@ def f_ev_c4(n00, n2m, n4m):
     m12s5 = _r4(f32(-12.0) * np.sqrt(f32(5.0)))
     s30x6 = _r4(np.sqrt(f32(30.0)) * f32(6.0)); s30xm6 = _r4(np.sqrt(f32(30.0)) * f32(-6.0))
     s10x2 = _r4(np.sqrt(f32(10.0)) * f32(2.0)); s10xm2 = _r4(np.sqrt(f32(10.0)) * f32(-2.0))
-    m3s3 = _r4(f32(-3.0) * np.sqrt(f32(3.0))); p3_15 = _r4(np.power(f32(3.0), f32(1.5)))
+    m3s3 = _r4(f32(-3.0) * np.sqrt(f32(3.0))); p3_15 = _r4(math.pow(3.0, 1.5))   # (3.0)**1.5: real(4) constant folded by gfortran (correctly rounded)
     ms7 = _r4(f32(-1.0) * np.sqrt(f32(7.0))); ms70 = _r4(f32(-1.0) * np.sqrt(f32(70.0)))
     p3s6 = _r4(f32(3.0) * np.sqrt(f32(6.0))); m3s6 = _r4(f32(-3.0) * np.sqrt(f32(6.0)))
     m4s5 = _r4(f32(-4.0) * np.sqrt(f32(5.0))); p2s5 = _r4(f32(2.0) * np.sqrt(f32(5.0)))

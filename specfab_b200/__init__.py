@@ -19,6 +19,8 @@ from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
 __all__ = ["init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
+           "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
+           "Eij_eigenframe_arr", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
 
 _state = {"L": None, "n": None}
@@ -122,6 +124,121 @@ def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.
 
 
 # ------------------------------------------------------------------------------------------
+# structure tensors, eigenframe, enhancement factors (host arrays)
+# ------------------------------------------------------------------------------------------
+
+def _nlm15(nlm):
+    """(N, >=15) complex -> Fortran-ordered (N, k) complex128 (only the l<=4 coefficients are read)"""
+    a = np.asarray(nlm, dtype=np.complex128)
+    if a.ndim != 2 or a.shape[1] < 15:
+        raise ValueError("expected nlm of shape (N, nlm_len>=15), got %s" % (a.shape,))
+    return np.asfortranarray(a[:, :15])
+
+
+def a2_arr(nlm):
+    """a2 of every node: (N,nlm_len) -> (N,3,3)          reference per node: src/specfabpy.f90:583-590"""
+    _need_init()
+    x = _nlm15(nlm)
+    N = x.shape[0]
+    out = np.empty((N, 3, 3), dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_a2_arr(x.ctypes.data, N, N, out.ctypes.data))
+    return out
+
+
+def a4_arr(nlm):
+    """a4 of every node: (N,nlm_len) -> (N,3,3,3,3)      reference per node: src/specfabpy.f90:592-599"""
+    _need_init()
+    x = _nlm15(nlm)
+    N = x.shape[0]
+    out = np.empty((N, 3, 3, 3, 3), dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_a4_arr(x.ctypes.data, N, N, out.ctypes.data))
+    return out
+
+
+def eig_arr(nlm):
+    """a2 eigenframe of every node -> (ei (N,3,3) with ei[p,i,:] the i-th eigenvector, lami (N,3)),
+    largest eigenvalue first            reference per node: src/specfabpy.f90:312-320"""
+    _need_init()
+    x = _nlm15(nlm)
+    N = x.shape[0]
+    ei = np.empty((N, 3, 3), dtype=np.float64, order="F")
+    lami = np.empty((N, 3), dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_eig_arr(x.ctypes.data, N, N, ei.ctypes.data, lami.ctypes.data))
+    return ei, lami
+
+
+def eigframe_arr(M, plane="ij"):
+    """eigframe_arr(M (N,3,3), plane) -> (ei, lami)        reference: src/specfabpy.f90:333-344"""
+    m = _farr(M, np.float64, (3, 3))
+    N = m.shape[0]
+    ei = np.empty((N, 3, 3), dtype=np.float64, order="F")
+    lami = np.empty((N, 3), dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_eigframe_arr(m.ctypes.data, N, str(plane).encode(), ei.ctypes.data, lami.ctypes.data))
+    return ei, lami
+
+
+def Eij_tranisotropic_arr(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_status=False):
+    """Eij_tranisotropic_arr(nlm (N,nlm_len), e1,e2,e3 (N,3), Eij_grain(2), alpha, n_grain) -> Eij (N,6)
+    reference: src/specfabpy.f90:474-486.  return_status adds the per-node SFB_ST_* flags."""
+    _need_init()
+    x = _nlm15(nlm)
+    N = x.shape[0]
+    es = [_farr(e, np.float64, (3,)) for e in (e1, e2, e3)]
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    if g.shape != (2,):
+        raise ValueError("Eij_grain must have 2 entries (Emm, Emt)")
+    out = np.empty((N, 6), dtype=np.float64, order="F")
+    st = np.zeros(N, dtype=np.int32)
+    _lib.check(_lib.load().sfb_Eij_tranisotropic_arr(x.ctypes.data, N, N, es[0].ctypes.data, es[1].ctypes.data, es[2].ctypes.data,
+                                                     g.ctypes.data, float(alpha), int(n_grain), out.ctypes.data, st.ctypes.data))
+    return (out, st) if return_status else out
+
+
+def Eij_eigenframe_arr(nlm, Eij_grain, alpha, n_grain, return_frame=False, return_status=False):
+    """Fused a2 -> eigenframe -> Eij_tranisotropic (eigenenhancements) of every node -> Eij (N,6)
+    [, ei (N,3,3), lami (N,3)] [, status].  Batches src/specfabpy/fenics/enhancementfactor.py:101-128."""
+    _need_init()
+    x = _nlm15(nlm)
+    N = x.shape[0]
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    out = np.empty((N, 6), dtype=np.float64, order="F")
+    ei = np.empty((N, 3, 3), dtype=np.float64, order="F")
+    lami = np.empty((N, 3), dtype=np.float64, order="F")
+    st = np.zeros(N, dtype=np.int32)
+    _lib.check(_lib.load().sfb_Eij_eigenframe_arr(x.ctypes.data, N, N, g.ctypes.data, float(alpha), int(n_grain), out.ctypes.data,
+                                                  ei.ctypes.data, lami.ctypes.data, st.ctypes.data))
+    res = (out,)
+    if return_frame:
+        res += (ei, lami)
+    if return_status:
+        res += (st,)
+    return res if len(res) > 1 else out
+
+
+# scalar (single-state) forms with the reference's exact signatures; they run the same kernels with N = 1
+def a2(nlm):
+    """reference: src/specfabpy.f90:583-590"""
+    return np.ascontiguousarray(a2_arr(np.asarray(nlm)[None, :])[0])
+
+
+def a4(nlm):
+    """reference: src/specfabpy.f90:592-599"""
+    return np.ascontiguousarray(a4_arr(np.asarray(nlm)[None, :])[0])
+
+
+def eig(nlm):
+    """reference: src/specfabpy.f90:312-320 -> (ei[3,3], lami[3])"""
+    ei, lami = eig_arr(np.asarray(nlm)[None, :])
+    return np.ascontiguousarray(ei[0]), np.ascontiguousarray(lami[0])
+
+
+def Eij_tranisotropic(nlm, e1, e2, e3, Eij_grain, alpha, n_grain):
+    """reference: src/specfabpy.f90:390-400 -> Eij[6]"""
+    return np.ascontiguousarray(Eij_tranisotropic_arr(np.asarray(nlm)[None, :], np.asarray(e1)[None, :], np.asarray(e2)[None, :],
+                                                      np.asarray(e3)[None, :], Eij_grain, alpha, n_grain)[0])
+
+
+# ------------------------------------------------------------------------------------------
 # device-resident API (torch tensors as memory handles; kernels run on torch's current stream)
 # ------------------------------------------------------------------------------------------
 
@@ -170,4 +287,44 @@ def step_arr_dev(nlm, ugrad, tau=None, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=
     o = _opts(dt, iota, zeta, nu, 0.0 if g0p else Gamma0, 0.0 if lamp else Lambda, terms, scheme, nsteps, g0p, lamp)
     _lib.check(lib.sfb_step_arr_dev(nlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
                                     tau.data_ptr() if tau is not None else None, N, C.byref(o), _stream_ptr()))
+    return out
+
+
+def a2_arr_dev(nlm, out=None):
+    """a2 of every node from a resident state: nlm (nlm_len,N) complex128 CUDA -> (3,3,N) float64 (Fortran (N,3,3))."""
+    import torch
+    _need_init()
+    N = nlm.shape[1]
+    if out is None:
+        out = torch.empty((3, 3, N), dtype=torch.float64, device=nlm.device)
+    _lib.check(_lib.load().sfb_a2_arr_dev(nlm.data_ptr(), N, N, out.data_ptr(), _stream_ptr()))
+    return out
+
+
+def Eij_tranisotropic_arr_dev(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, out=None, status=None):
+    """Eij in given frames: nlm (nlm_len,N), e1/e2/e3 (3,N) float64 CUDA (Fortran (N,3)) -> (6,N)."""
+    import torch
+    _need_init()
+    N = nlm.shape[1]
+    if out is None:
+        out = torch.empty((6, N), dtype=torch.float64, device=nlm.device)
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    _lib.check(_lib.load().sfb_Eij_tranisotropic_arr_dev(nlm.data_ptr(), N, N, e1.data_ptr(), e2.data_ptr(), e3.data_ptr(), g.ctypes.data,
+                                                         float(alpha), int(n_grain), out.data_ptr(),
+                                                         status.data_ptr() if status is not None else None, _stream_ptr()))
+    return out
+
+
+def Eij_eigenframe_arr_dev(nlm, Eij_grain, alpha, n_grain, out=None, ei=None, lami=None, status=None):
+    """Fused a2 -> eigenframe -> Eij on a resident state -> (6,N) float64 CUDA tensor."""
+    import torch
+    _need_init()
+    N = nlm.shape[1]
+    if out is None:
+        out = torch.empty((6, N), dtype=torch.float64, device=nlm.device)
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    _lib.check(_lib.load().sfb_Eij_eigenframe_arr_dev(nlm.data_ptr(), N, N, g.ctypes.data, float(alpha), int(n_grain), out.data_ptr(),
+                                                      ei.data_ptr() if ei is not None else None,
+                                                      lami.data_ptr() if lami is not None else None,
+                                                      status.data_ptr() if status is not None else None, _stream_ptr()))
     return out

@@ -40,6 +40,19 @@ SIGNATURES = {
     "sfb_build_info": (C.c_char_p, []),
     "sfb_step_arr": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(StepOpts)]),
     "sfb_step_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, C.POINTER(StepOpts), _P]),
+    "sfb_a2_arr": (C.c_int, [_P, _I64, _I64, _P]),
+    "sfb_a2_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "sfb_a4_arr": (C.c_int, [_P, _I64, _I64, _P]),
+    "sfb_a4_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "sfb_eig_arr": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "sfb_eig_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P, _P]),
+    "sfb_eigframe_arr": (C.c_int, [_P, _I64, C.c_char_p, _P, _P]),
+    "sfb_eigframe_arr_dev": (C.c_int, [_P, _I64, _I64, C.c_char_p, _P, _P, _P]),
+    "sfb_Eij_tranisotropic_arr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
+    "sfb_Eij_tranisotropic_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P]),
+    "sfb_Eij_eigenframe_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P]),
+    "sfb_Eij_eigenframe_arr_dev": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P]),
+    "sfb_set_variant": (C.c_int, [C.c_int]),
     "sfb_dev_malloc": (C.c_int, [C.POINTER(_P), _I64]),
     "sfb_dev_free": (C.c_int, [_P]),
     "sfb_memcpy_h2d": (C.c_int, [_P, _P, _I64]),

@@ -28,16 +28,24 @@ CFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 ALL_L = [4, 6, 8, 10, 12, 14, 16, 18, 20]
 
 # tuning table: (L, ddrx) -> (roles R, tile nodes TN, min CTAs/SM for __launch_bounds__)
+# variant 0 is the default; extra variants (EXTRA) are selectable with sfb_set_variant() for tuning runs
+EXTRA = {
+    # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]
+    (8, 0): [(1, 2, 32, 2, "imm", False), (2, 1, 64, 1, "cbank", True), (4, 2, 64, 1, "cbank", True)],
+    (8, 1): [(1, 2, 32, 2, "imm", False), (2, 1, 64, 1, "cbank", True), (4, 2, 64, 1, "cbank", True)],
+}
+# default variant: single instruction stream per CTA (R = 1) kept in lockstep -- ncu showed the
+# multi-role / multi-CTA layouts stall on instruction fetch (profiles/r01_notes.md)
 TUNE = {
-    (4, 0): (1, 32, 2), (4, 1): (1, 32, 2),
-    (6, 0): (1, 32, 2), (6, 1): (2, 32, 2),
-    (8, 0): (2, 32, 2), (8, 1): (2, 32, 2),
-    (10, 0): (2, 32, 2), (10, 1): (2, 32, 2),
-    (12, 0): (2, 32, 2), (12, 1): (2, 32, 2),
-    (14, 0): (2, 16, 2), (14, 1): (4, 16, 2),
-    (16, 0): (4, 16, 2), (16, 1): (4, 16, 2),
-    (18, 0): (4, 16, 2), (18, 1): (4, 16, 2),
-    (20, 0): (4, 16, 2), (20, 1): (4, 16, 2),
+    (4, 0): (1, 64, 1, "imm", True), (4, 1): (1, 64, 1, "imm", True),
+    (6, 0): (1, 64, 1, "imm", True), (6, 1): (1, 64, 1, "imm", True),
+    (8, 0): (1, 64, 1, "imm", True), (8, 1): (1, 64, 1, "imm", True),
+    (10, 0): (1, 32, 1, "imm", True), (10, 1): (2, 32, 1, "imm", True),
+    (12, 0): (1, 32, 1, "imm", True), (12, 1): (2, 32, 1, "imm", True),
+    (14, 0): (2, 16, 1, "imm", True), (14, 1): (4, 16, 1, "imm", True),
+    (16, 0): (4, 16, 1, "imm", True), (16, 1): (4, 16, 1, "imm", True),
+    (18, 0): (4, 16, 1, "imm", True), (18, 1): (4, 16, 1, "imm", True),
+    (20, 0): (4, 16, 1, "imm", True), (20, 1): (4, 16, 1, "imm", True),
 }
 
 
@@ -56,24 +64,27 @@ def generate(Ls):
     units, metas = [], []
     for L in Ls:
         for dd in (0, 1):
-            R, TN, MINB = TUNE[(L, dd)]
-            tag = "L%d_%s" % (L, "ddrx" if dd else "lrot")
-            body, meta = emit_step.emit(L, dd, R, TN)
-            _write_if_changed(os.path.join(GEN, "apply_%s.inc" % tag), body)
-            cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_R %d\n#define SFB_TN %d\n#define SFB_MINB %d\n'
-                  '#define SFB_NAME sfb_launch_step_%s\n#define SFB_APPLY_INC "gen/apply_%s.inc"\n'
-                  '#include "sfb_step_kernel.cuh"\n' % (L, dd, R, TN, MINB, tag, tag))
-            path = os.path.join(GEN, "step_%s.cu" % tag)
-            _write_if_changed(path, cu)
-            units.append(path)
-            meta["tag"] = tag
-            metas.append(meta)
+            R, TN, MINB, cm0, sy0 = TUNE[(L, dd)]
+            variants = [(0, R, TN, MINB, cm0, sy0)] + (EXTRA.get((L, dd), []) if os.environ.get("SFB_EXTRA_VARIANTS", "1") == "1" else [])
+            for (vid, R, TN, MINB, cmode, sync) in variants:
+                tag = "L%d_%s" % (L, "ddrx" if dd else "lrot") + ("_v%d" % vid if vid else "")
+                body, tab, meta = emit_step.emit(L, dd, R, TN, cmode, sync)
+                _write_if_changed(os.path.join(GEN, "apply_%s.inc" % tag), body)
+                cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_R %d\n#define SFB_TN %d\n#define SFB_MINB %d\n'
+                      '#define SFB_NAME sfb_launch_step_%s\n#define SFB_APPLY_INC "gen/apply_%s.inc"\n%s'
+                      '#include "sfb_step_kernel.cuh"\n' % (L, dd, R, TN, MINB, tag, tag, tab))
+                path = os.path.join(GEN, "step_%s.cu" % tag)
+                _write_if_changed(path, cu)
+                units.append(path)
+                meta["tag"] = tag
+                meta["variant"] = vid
+                metas.append(meta)
     reg = ["// GENERATED registry of step launchers"]
     for m in metas:
         reg.append('extern "C" cudaError_t sfb_launch_step_%s(const SfbStepParams&, const SfbRegConst&, cudaStream_t);' % m["tag"])
     reg.append("static const SfbStepEntry kStepRegistry[] = {")
     for m in metas:
-        reg.append("  {%d, %d, %d, %d, %d, sfb_launch_step_%s}," % (m["L"], m["ddrx"], m["R"], m["TN"], m["dfma_node"], m["tag"]))
+        reg.append("  {%d, %d, %d, %d, %d, %d, sfb_launch_step_%s}," % (m["L"], m["ddrx"], m["variant"], m["R"], m["TN"], m["dfma_node"], m["tag"]))
     reg.append("};")
     _write_if_changed(os.path.join(GEN, "registry.inc"), "\n".join(reg) + "\n")
     _write_if_changed(os.path.join(GEN, "tables.inc"), emit_tables.emit())
@@ -118,7 +129,7 @@ def build(Ls=None, jobs=None, verbose=False):
     Ls = Ls or ALL_L
     jobs = jobs or max(1, (os.cpu_count() or 2))
     units, metas = generate(Ls)
-    units = units + [os.path.join(CSRC, "sfb_api.cu")]
+    units = units + [os.path.join(CSRC, "sfb_api.cu"), os.path.join(CSRC, "sfb_fields.cu")]
     objs = []
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
         for obj, dt, log in ex.map(lambda s: compile_one(s, verbose), units):

@@ -7,10 +7,19 @@
 #include <vector>
 
 #include "sfb_common.cuh"
+#include "sfb_fields.cuh"
 #include "specfab_b200.h"
 
+cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
+                           long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
+                           long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
+                           int* status, cudaStream_t st);
+
 struct SfbStepEntry {
-    int L, ddrx, R, TN, dfma_node;
+    int L, ddrx, variant, R, TN, dfma_node;
     sfb_step_launch_fn fn;
 };
 #include "gen/registry.inc"
@@ -47,10 +56,15 @@ const double kNu[9] = {1.9879322126397958, 3.0011508426238862, 5.749806992135238
                        10.6068117205577668, 13.3591023418822363, 15.3094482670021108, 16.4844589176829217,
                        19.9467342880730136};
 
+int g_variant = 0;   // tuning knob (sfb_set_variant); falls back to variant 0 when absent
 const SfbStepEntry* find_step(int L, int ddrx) {
+    const SfbStepEntry* def = nullptr;
     for (const auto& e : kStepRegistry)
-        if (e.L == L && e.ddrx == ddrx) return &e;
-    return nullptr;
+        if (e.L == L && e.ddrx == ddrx) {
+            if (e.variant == g_variant) return &e;
+            if (e.variant == 0) def = &e;
+        }
+    return def;
 }
 
 // ---- host-pointer staging: per-thread ring of device chunk buffers -------------------------
@@ -125,7 +139,7 @@ const char* sfb_build_info(void) {
         bool first = true;
         for (const auto& e : kStepRegistry) {
             char b[160];
-            snprintf(b, sizeof b, "%s{\"L\":%d,\"ddrx\":%d,\"roles\":%d,\"tile\":%d,\"dfma_per_node_rhs\":%d}", first ? "" : ",", e.L, e.ddrx, e.R, e.TN, e.dfma_node);
+            snprintf(b, sizeof b, "%s{\"L\":%d,\"ddrx\":%d,\"variant\":%d,\"roles\":%d,\"tile\":%d,\"dfma_per_node_rhs\":%d}", first ? "" : ",", e.L, e.ddrx, e.variant, e.R, e.TN, e.dfma_node);
             s += b;
             first = false;
         }
@@ -235,6 +249,212 @@ int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
     }
     for (auto& s : g_stage.s)
         if (s.st) CK(cudaStreamSynchronize(s.st));
+    return SFB_OK;
+}
+
+int sfb_set_variant(int v) { g_variant = v; return SFB_OK; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// a2 / a4 / eig / Eij
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DevTmp {     // scratch device allocation of the host-pointer entry points
+    void* p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+int basic_check(const void* nlm, int64_t N, int64_t ld) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    if (N > 0 && !nlm) return fail(SFB_EINVAL, "null array");
+    return SFB_OK;
+}
+int plane_code(const char* plane) {
+    if (!plane) return -1;
+    if (plane[0] == 'i' && plane[1] == 'j') return 0;
+    if (plane[0] == 'x' && plane[1] == 'y') return 1;
+    if (plane[0] == 'x' && plane[1] == 'z') return 2;
+    return -1;
+}
+// src/rheologies.f90:123-135 with d = 3, evaluated on the host with libm pow (like the reference)
+void rheo_params(const double E[2], double n, int ef, double& cI, double& cM, double& cL) {
+    const int d = 3;
+    const double ne = ef * 2 / (n + 1);
+    cI = (pow(E[0], ne) - 1) / (d - 1);
+    cM = (d * (pow(E[0], ne) + 1) - 2) / (d - 1) - 2 * pow(E[1], ne);
+    cL = pow(E[1], ne) - 1;
+}
+int make_coef(const double* Eij_grain, double alpha, int n_grain, sfb::EijCoef& K) {
+    if (!Eij_grain) return fail(SFB_EINVAL, "null Eij_grain");
+    if (n_grain != 1) return fail(SFB_EINVAL, "only n_grain = 1 is implemented (n'=3 Sachs needs a6/a8: SURVEY.md 8f-4)");
+    rheo_params(Eij_grain, (double)n_grain, 1, K.sA, K.sB, K.sC);
+    rheo_params(Eij_grain, (double)n_grain, -1, K.tA, K.tB, K.tC);
+    K.s_iso = 1 + 2.0 / 15 * K.sB + 2.0 / 3 * K.sC;
+    K.t_iso = 1 + 2.0 / 15 * K.tB + 2.0 / 3 * K.tC;
+    K.alpha = alpha;
+    return SFB_OK;
+}
+// copy the first `rows` coefficient rows of a host nlm(N,n) to a packed device array [rows][N]
+int stage_rows(DevTmp& d, const double* nlm, int64_t N, int64_t ld, int rows) {
+    CK(d.alloc((size_t)rows * N * 16));
+    CK(cudaMemcpy2D(d.p, (size_t)N * 16, nlm, (size_t)ld * 16, (size_t)N * 16, rows, cudaMemcpyHostToDevice));
+    return SFB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sfb_a2_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a2, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (N && !a2) return fail(SFB_EINVAL, "null output");
+    CK(sfb_launch_a2(reinterpret_cast<const double2*>(nlm), N, ld, a2, N, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_a2_arr(const double* nlm, int64_t N, int64_t ld, double* a2) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc || N == 0) return rc;
+    DevTmp in, out;
+    if ((rc = stage_rows(in, nlm, N, ld, 6))) return rc;
+    CK(out.alloc((size_t)N * 9 * 8));
+    if ((rc = sfb_a2_arr_dev(in.as<double>(), N, N, out.as<double>(), nullptr))) return rc;
+    CK(cudaMemcpy(a2, out.p, (size_t)N * 9 * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_a4_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a4, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (N && !a4) return fail(SFB_EINVAL, "null output");
+    CK(sfb_launch_a4(reinterpret_cast<const double2*>(nlm), N, ld, a4, N, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_a4_arr(const double* nlm, int64_t N, int64_t ld, double* a4) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc || N == 0) return rc;
+    DevTmp in, out;
+    if ((rc = stage_rows(in, nlm, N, ld, 15))) return rc;
+    CK(out.alloc((size_t)N * 81 * 8));
+    if ((rc = sfb_a4_arr_dev(in.as<double>(), N, N, out.as<double>(), nullptr))) return rc;
+    CK(cudaMemcpy(a4, out.p, (size_t)N * 81 * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_eig_arr_dev(const double* nlm, int64_t N, int64_t ld, double* ei, double* lami, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (N && (!ei || !lami)) return fail(SFB_EINVAL, "null output");
+    CK(sfb_launch_eig(reinterpret_cast<const double2*>(nlm), nullptr, N, ld, 0, ei, lami, N, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_eig_arr(const double* nlm, int64_t N, int64_t ld, double* ei, double* lami) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc || N == 0) return rc;
+    DevTmp in, o1, o2;
+    if ((rc = stage_rows(in, nlm, N, ld, 6))) return rc;
+    CK(o1.alloc((size_t)N * 9 * 8));
+    CK(o2.alloc((size_t)N * 3 * 8));
+    if ((rc = sfb_eig_arr_dev(in.as<double>(), N, N, o1.as<double>(), o2.as<double>(), nullptr))) return rc;
+    CK(cudaMemcpy(ei, o1.p, (size_t)N * 9 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lami, o2.p, (size_t)N * 3 * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_eigframe_arr_dev(const double* M, int64_t N, int64_t ld, const char* plane, double* ei, double* lami, void* stream) {
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    const int pc = plane_code(plane);
+    if (pc < 0) return fail(SFB_EINVAL, "eigframe: argument \"plane\" was not any of ij,xy,xz");   // src/frames.f90:48
+    if (N == 0) return SFB_OK;
+    if (!M || !ei || !lami) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_eig(nullptr, M, N, ld, pc, ei, lami, N, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_eigframe_arr(const double* M, int64_t N, const char* plane, double* ei, double* lami) {
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (plane_code(plane) < 0) return fail(SFB_EINVAL, "eigframe: argument \"plane\" was not any of ij,xy,xz");
+    if (N == 0) return SFB_OK;
+    if (!M || !ei || !lami) return fail(SFB_EINVAL, "null array");
+    DevTmp in, o1, o2;
+    CK(in.alloc((size_t)N * 9 * 8));
+    CK(cudaMemcpy(in.p, M, (size_t)N * 9 * 8, cudaMemcpyHostToDevice));
+    CK(o1.alloc((size_t)N * 9 * 8));
+    CK(o2.alloc((size_t)N * 3 * 8));
+    int rc = sfb_eigframe_arr_dev(in.as<double>(), N, N, plane, o1.as<double>(), o2.as<double>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(ei, o1.p, (size_t)N * 9 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lami, o2.p, (size_t)N * 3 * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_Eij_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
+                                  const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    sfb::EijCoef K;
+    if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
+    if (N == 0) return SFB_OK;
+    if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_eij(reinterpret_cast<const double2*>(nlm), N, ld, e1, e2, e3, N, K, Eij, N, nullptr, nullptr, status, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
+                              const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    sfb::EijCoef K;
+    if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
+    if (N == 0) return SFB_OK;
+    if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
+    DevTmp in, de, out, ds;
+    if ((rc = stage_rows(in, nlm, N, ld, 15))) return rc;
+    CK(de.alloc((size_t)N * 9 * 8));
+    CK(cudaMemcpy(de.as<double>(), e1, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(de.as<double>() + 3 * N, e2, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(de.as<double>() + 6 * N, e3, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(out.alloc((size_t)N * 6 * 8));
+    CK(ds.alloc((size_t)N * 4));
+    rc = sfb_Eij_tranisotropic_arr_dev(in.as<double>(), N, N, de.as<double>(), de.as<double>() + 3 * N, de.as<double>() + 6 * N,
+                                       Eij_grain, alpha, n_grain, out.as<double>(), ds.as<int32_t>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
+    if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                               double* Eij, double* ei, double* lami, int32_t* status, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    sfb::EijCoef K;
+    if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
+    if (N == 0) return SFB_OK;
+    if (!Eij) return fail(SFB_EINVAL, "null array");
+    if ((ei == nullptr) != (lami == nullptr)) return fail(SFB_EINVAL, "ei and lami must both be given or both be NULL");
+    CK(sfb_launch_eij(reinterpret_cast<const double2*>(nlm), N, ld, nullptr, nullptr, nullptr, 0, K, Eij, N, ei, lami, status, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                           double* Eij, double* ei, double* lami, int32_t* status) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    sfb::EijCoef K;
+    if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
+    if (N == 0) return SFB_OK;
+    if (!Eij) return fail(SFB_EINVAL, "null array");
+    if ((ei == nullptr) != (lami == nullptr)) return fail(SFB_EINVAL, "ei and lami must both be given or both be NULL");
+    DevTmp in, out, o1, o2, ds;
+    if ((rc = stage_rows(in, nlm, N, ld, 15))) return rc;
+    CK(out.alloc((size_t)N * 6 * 8));
+    CK(o1.alloc((size_t)N * 9 * 8));
+    CK(o2.alloc((size_t)N * 3 * 8));
+    CK(ds.alloc((size_t)N * 4));
+    rc = sfb_Eij_eigenframe_arr_dev(in.as<double>(), N, N, Eij_grain, alpha, n_grain, out.as<double>(), o1.as<double>(), o2.as<double>(),
+                                    ds.as<int32_t>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
+    if (ei) {
+        CK(cudaMemcpy(ei, o1.p, (size_t)N * 9 * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(lami, o2.p, (size_t)N * 3 * 8, cudaMemcpyDeviceToHost));
+    }
+    if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }
 

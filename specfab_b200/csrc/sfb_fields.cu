@@ -1,0 +1,158 @@
+// Kernels + launchers for a2 / a4 / eigenframe / Eij on batches of nodes (thread per node).
+#include "sfb_fields.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ void load_m_ge0(const double2* __restrict__ nlm, long long ld, long long p,
+                                           double2& n00, double2 n2[3], double2 n4[5]) {
+    n00 = nlm[p];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];     // n_2^m at 0-based index 3+m
+#pragma unroll
+    for (int m = 0; m < 5; ++m) n4[m] = nlm[(long long)(10 + m) * ld + p];    // n_4^m at 0-based index 10+m
+}
+
+__device__ __forceinline__ void a2_from(double2 n00, const double2 n2[3], double a[3][3]) {
+    double a2v[6];
+    sfb::ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
+    // src/moments.f90:37-44 returns f_ev_c2 directly (no Mandel round trip): undo the sqrt(2) scaling exactly
+    // by recomputing the off-diagonals from the same expressions
+    const double2 h1 = sfb::cdiv(n2[1], n00), h2 = sfb::cdiv(n2[2], n00);
+    const double s215 = 0.3651483716701107;
+    a[0][0] = a2v[0]; a[1][1] = a2v[1]; a[2][2] = a2v[2];
+    a[0][1] = a[1][0] = s215 * (-h2.y);
+    a[0][2] = a[2][0] = s215 * (-h1.x);
+    a[1][2] = a[2][1] = s215 * (h1.y);
+}
+
+__global__ void __launch_bounds__(kBlock) a2_kernel(const double2* __restrict__ nlm, long long N, long long ld,
+                                                    double* __restrict__ out, long long ldo) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double2 n00 = nlm[p], n2[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];
+    double a[3][3];
+    a2_from(n00, n2, a);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[(long long)(i + 3 * k) * ldo + p] = a[i][k];
+}
+
+__global__ void __launch_bounds__(kBlock) a4_kernel(const double2* __restrict__ nlm, long long N, long long ld,
+                                                    double* __restrict__ out, long long ldo) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double2 n00 = nlm[p], n2[5], n4[9];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) n2[m] = nlm[(long long)(1 + m) * ld + p];
+#pragma unroll
+    for (int m = 0; m < 9; ++m) n4[m] = nlm[(long long)(6 + m) * ld + p];
+    double u[15];
+    sfb::ev_c4_unique(n00, n2, n4, u);
+    // a4(N,3,3,3,3) Fortran order: plane index a + 3b + 9c + 27d
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    int q = sfb::a4_unique_index(a, b, c, d);
+                    // reference quirk: src/include/ev_c4__body.f90:78  ev(3,2,1,2)=ev(1,2,3,3)
+                    if (a == 2 && b == 1 && c == 0 && d == 1) q = 8;
+                    out[(long long)(a + 3 * b + 9 * c + 27 * d) * ldo + p] = u[q];
+                }
+}
+
+// eig(nlm) (mode 0, src/frames.f90:14-22) or eigframe(M, plane) (mode 1, src/frames.f90:24-60)
+__global__ void __launch_bounds__(kBlock) eig_kernel(const double2* __restrict__ nlm, const double* __restrict__ M,
+                                                     long long N, long long ld, int plane,
+                                                     double* __restrict__ ei, double* __restrict__ lami, long long ldo) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double a[3][3];
+    if (nlm) {
+        double2 n00 = nlm[p], n2[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];
+        a2_from(n00, n2, a);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a[i][k] = M[(long long)(i + 3 * k) * ld + p];
+    }
+    double e[3][3], lam[3];
+    sfb::eigframe(a, plane, e, lam);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        lami[(long long)i * ldo + p] = lam[i];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) ei[(long long)(i + 3 * x) * ldo + p] = e[i][x];   // ei(N,3,3): (p,i,x)
+    }
+}
+
+// Eij_tranisotropic_arr (src/specfabpy.f90:474-486).  frame given (e1,e2,e3 each (N,3) Fortran order)
+// or, when e1 == nullptr, computed as the a2 eigenframe of the node (fused a2 -> eig -> Eij).
+__global__ void __launch_bounds__(kBlock) eij_kernel(const double2* __restrict__ nlm, long long N, long long ld,
+                                                     const double* __restrict__ e1, const double* __restrict__ e2,
+                                                     const double* __restrict__ e3, long long lde, sfb::EijCoef K,
+                                                     double* __restrict__ Eij, long long ldo,
+                                                     double* __restrict__ ei_out, double* __restrict__ lam_out,
+                                                     int* __restrict__ status) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double2 n00, n2[3], n4[5];
+    load_m_ge0(nlm, ld, p, n00, n2, n4);
+    double e[3][3];
+    if (e1) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) { e[0][x] = e1[(long long)x * lde + p]; e[1][x] = e2[(long long)x * lde + p]; e[2][x] = e3[(long long)x * lde + p]; }
+    } else {
+        double a[3][3], lam[3];
+        a2_from(n00, n2, a);
+        sfb::eigframe(a, 0, e, lam);
+        if (ei_out) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                lam_out[(long long)i * ldo + p] = lam[i];
+#pragma unroll
+                for (int x = 0; x < 3; ++x) ei_out[(long long)(i + 3 * x) * ldo + p] = e[i][x];
+            }
+        }
+    }
+    double E[6];
+    const int st = sfb::eij_tranisotropic(n00, n2, n4, e, K, E);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Eij[(long long)q * ldo + p] = E[q];
+    if (status) status[p] = st;
+}
+
+inline unsigned nblk(long long N) { return (unsigned)((N + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st) {
+    if (N > 0) a2_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, out, ldo);
+    return cudaGetLastError();
+}
+cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st) {
+    if (N > 0) a4_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, out, ldo);
+    return cudaGetLastError();
+}
+cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
+                           long long ldo, cudaStream_t st) {
+    if (N > 0) eig_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, M, N, ld, plane, ei, lami, ldo);
+    return cudaGetLastError();
+}
+cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
+                           long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
+                           int* status, cudaStream_t st) {
+    if (N > 0) eij_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+    return cudaGetLastError();
+}

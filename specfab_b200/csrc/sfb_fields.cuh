@@ -1,0 +1,342 @@
+// Per-node field evaluations on the resident spectral state: a2, a4, eigenframe, Eij.
+// One thread per node, node-contiguous (coalesced) loads of the first 15 coefficient rows.
+// Reference: src/moments.f90:37-55 (a2, a4), src/frames.f90:14-80 (eig, eigframe, eig3),
+// src/enhancementfactors.f90:23-69,398-413 (Eij_tranisotropic, Evw, tau_vv/vw),
+// src/homogenizations.f90:69-116,145-258 (Sachs / Taylor, n'=1), src/rheologies.f90:123-135.
+#pragma once
+#include "sfb_common.cuh"
+#include "sfb_moments.cuh"
+#include "specfab_b200.h"
+
+namespace sfb {
+
+// ---------------------------------------------------------------------------------------------
+// a4 with the reference's real(4) constants (src/include/ev_c4__body.f90:1-94): 15 unique entries
+// u[q], q indexing the sorted index quadruples
+//  0:1111 1:1112 2:1113 3:1122 4:1123 5:1133 6:1222 7:1223 8:1233 9:1333 10:2222 11:2223 12:2233 13:2333 14:3333
+// n2[0..4] <-> m=-2..2, n4[0..8] <-> m=-4..4.  Only REAL(...) of each complex sum is needed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ev_c4_unique(double2 n00, const double2 n2[5], const double2 n4[9], double u[15]) {
+    // real(4) constants promoted to double (oracle/specfab_oracle.py f_ev_c4)
+    const double s5 = 0x1.1e377ap+1, s30 = 0x1.5e8adep+2, s10 = 0x1.94c584p+1, s70 = 0x1.0bbb3p+3, s2 = 0x1.6a09e6p+0,
+                 s3 = 0x1.bb67aep+0, s7 = 0x1.52a7fap+1, s6 = 0x1.3988e2p+1;
+    const double m12s5 = -0x1.ad5338p+4, s30x6 = 0x1.06e826p+5, s10x2 = 0x1.94c584p+2;
+    const double m3s3 = -0x1.4c8dc2p+2, p3_15 = 0x1.4c8dc2p+2;
+    const double p3s6 = 0x1.d64d54p+2, m4s5 = -0x1.1e377ap+3, p2s5 = 0x1.1e377ap+2, p12s5 = 0x1.ad5338p+4;
+#define RE2(m) n2[(m) + 2].x
+#define IM2(m) n2[(m) + 2].y
+#define RE4(m) n4[(m) + 4].x
+#define IM4(m) n4[(m) + 4].y
+    // entries of the form REAL(Z / s5)
+    u[0] = (42.0 * n00.x + m12s5 * RE2(0) + s30x6 * RE2(-2) + s30x6 * RE2(2) + 6.0 * RE4(0) + (-s10x2) * RE4(-2) + (-s10x2) * RE4(2) + s70 * RE4(-4) + s70 * RE4(4)) / s5;
+    u[3] = (14.0 * n00.x + m4s5 * RE2(0) + 2.0 * RE4(0) + (-s70) * RE4(-4) + (-s70) * RE4(4)) / s5;
+    u[5] = (14.0 * n00.x + p2s5 * RE2(0) + s30 * RE2(-2) + s30 * RE2(2) + -8.0 * RE4(0) + s10x2 * RE4(-2) + s10x2 * RE4(2)) / s5;
+    u[10] = (42.0 * n00.x + m12s5 * RE2(0) + (-s30x6) * RE2(-2) + (-s30x6) * RE2(2) + 6.0 * RE4(0) + s10x2 * RE4(-2) + s10x2 * RE4(2) + s70 * RE4(-4) + s70 * RE4(4)) / s5;
+    u[12] = (14.0 * n00.x + p2s5 * RE2(0) + (-s30) * RE2(-2) + (-s30) * RE2(2) + -8.0 * RE4(0) + (-s10x2) * RE4(-2) + (-s10x2) * RE4(2)) / s5;
+    u[14] = (2.0 * (21.0 * n00.x + p12s5 * RE2(0) + 8.0 * RE4(0))) / s5;
+    // entries REAL(Z)
+    u[2] = p3s6 * RE2(-1) + (-p3s6) * RE2(1) + -3.0 * RE4(-1) + 3.0 * RE4(1) + s7 * RE4(-3) + (-s7) * RE4(3);
+    u[7] = s6 * RE2(-1) + (-s6) * RE2(1) + -1.0 * RE4(-1) + RE4(1) + (-s7) * RE4(-3) + s7 * RE4(3);
+    u[9] = p3s6 * RE2(-1) + (-p3s6) * RE2(1) + 4.0 * RE4(-1) + -4.0 * RE4(1);
+    // entries REAL((0,c) * Z) = -c * Im(Z)
+    u[1] = -(s2 * (m3s3 * IM2(-2) + p3_15 * IM2(2) + IM4(-2) + -1.0 * IM4(2) + (-s7) * IM4(-4) + s7 * IM4(4)));
+    u[6] = -(s2 * (m3s3 * IM2(-2) + p3_15 * IM2(2) + IM4(-2) + -1.0 * IM4(2) + s7 * IM4(-4) + (-s7) * IM4(4)));
+    u[8] = -(s2 * ((-s3) * IM2(-2) + s3 * IM2(2) + -2.0 * IM4(-2) + 2.0 * IM4(2)));
+    u[4] = -((-s6) * IM2(-1) + (-s6) * IM2(1) + IM4(-1) + IM4(1) + (-s7) * IM4(-3) + (-s7) * IM4(3));
+    u[11] = -((-p3s6) * IM2(-1) + (-p3s6) * IM2(1) + 3.0 * IM4(-1) + 3.0 * IM4(1) + s7 * IM4(-3) + s7 * IM4(3));
+    u[13] = -((-p3s6) * IM2(-1) + (-p3s6) * IM2(1) + 4.0 * (-1.0 * IM4(-1) + -1.0 * IM4(1)));
+#undef RE2
+#undef IM2
+#undef RE4
+#undef IM4
+    const double k = 0x1.35370ba079db2p-5;        // Sqrt(Pi/5.)/21.
+    const double c0 = 0x1.c5bf891b4ef6ap+1 * n00.x;  // f_ev_c0
+#pragma unroll
+    for (int q = 0; q < 15; ++q) u[q] = u[q] * k / c0;
+}
+
+// index of the sorted quadruple (a<=b<=c<=d), values 0..2, in the 15-entry list above
+__host__ __device__ __forceinline__ int a4_unique_index(int a, int b, int c, int d) {
+    // sort 4 small ints
+    int t;
+#define SW(x, y) if (x > y) { t = x; x = y; y = t; }
+    SW(a, b) SW(c, d) SW(a, c) SW(b, d) SW(b, c)
+#undef SW
+    const int code = a * 27 + b * 9 + c * 3 + d;
+    switch (code) {
+        case 0: return 0;  case 1: return 1;  case 2: return 2;  case 4: return 3;  case 5: return 4;
+        case 8: return 5;  case 13: return 6; case 14: return 7; case 17: return 8; case 26: return 9;
+        case 40: return 10; case 41: return 11; case 44: return 12; case 53: return 13; default: return 14;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// symmetric 3x3 eigen decomposition (cyclic Jacobi), eigenvalues descending, V[:,i] eigenvectors.
+// Replaces LAPACK dsyev('V','U') of src/frames.f90:75; eigenvector signs / degenerate bases are
+// implementation-defined there too: here the largest |component| is made positive.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void eig3_sym(const double m[3][3], double w[3], double V[3][3]) {
+    double a[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { a[i][j] = m[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+    a[1][0] = a[0][1]; a[2][0] = a[0][2]; a[2][1] = a[1][2];   // 'U': upper triangle is the input
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        const double dia = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+        if (off <= 1e-17 * dia || off == 0.0) break;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;
+            const double apq = a[p][q];
+            if (apq != 0.0) {
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                const int k = 3 - p - q;
+                const double akp = a[k][p], akq = a[k][q];
+                a[p][p] -= t * apq;
+                a[q][q] += t * apq;
+                a[p][q] = a[q][p] = 0.0;
+                a[k][p] = a[p][k] = c * akp - s * akq;
+                a[k][q] = a[q][k] = s * akp + c * akq;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double vip = V[i][p], viq = V[i][q];
+                    V[i][p] = c * vip - s * viq;
+                    V[i][q] = s * vip + c * viq;
+                }
+            }
+        }
+    }
+    w[0] = a[0][0]; w[1] = a[1][1]; w[2] = a[2][2];
+    // sort descending (largest eigenvalue first, src/frames.f90:76-79)
+#define SWAPCOL(i, j)                                                     \
+    if (w[i] < w[j]) {                                                    \
+        double t = w[i]; w[i] = w[j]; w[j] = t;                           \
+        for (int r = 0; r < 3; ++r) { t = V[r][i]; V[r][i] = V[r][j]; V[r][j] = t; } \
+    }
+    SWAPCOL(0, 1) SWAPCOL(0, 2) SWAPCOL(1, 2)
+#undef SWAPCOL
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int im = 0;
+        if (fabs(V[1][i]) > fabs(V[im][i])) im = 1;
+        if (fabs(V[2][i]) > fabs(V[im][i])) im = 2;
+        if (V[im][i] < 0) { V[0][i] = -V[0][i]; V[1][i] = -V[1][i]; V[2][i] = -V[2][i]; }
+    }
+}
+
+// eigframe(M, plane): src/frames.f90:24-60.  plane: 0 'ij', 1 'xy', 2 'xz'.  ei[i][:] = i-th eigenvector.
+__device__ __forceinline__ void eigframe(const double m[3][3], int plane, double ei[3][3], double lam[3]) {
+    double V[3][3], w[3];
+    eig3_sym(m, w, V);
+    int sort[3] = {0, 1, 2};
+    if (plane != 0) {
+        const int k = (plane == 1) ? 2 : 1;
+        int imax = 0;
+        if (fabs(V[k][1]) > fabs(V[k][imax])) imax = 1;
+        if (fabs(V[k][2]) > fabs(V[k][imax])) imax = 2;
+        if (imax == 0) { sort[0] = 1; sort[1] = 2; sort[2] = 0; }
+        if (imax == 1) { sort[0] = 0; sort[1] = 2; sort[2] = 1; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        lam[i] = w[sort[i]];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) ei[i][x] = V[x][sort[i]];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eij_tranisotropic, n'=1
+// ---------------------------------------------------------------------------------------------
+struct EijCoef {          // host-evaluated scalars (libm pow like the reference): src/rheologies.f90:123-135
+    double sA, sB, sC;    // Sachs  (ef = +1)
+    double tA, tB, tC;    // Taylor (ef = -1)
+    double s_iso;         // 1 + 2/15*sB + 2/3*sC        src/homogenizations.f90:206
+    double t_iso;         // 1 + 2/15*tB + 2/3*tC        src/homogenizations.f90:235
+    double alpha;
+};
+
+__device__ __forceinline__ void mat_to_vec(const double t[3][3], double v[6]) {
+    v[0] = t[0][0]; v[1] = t[1][1]; v[2] = t[2][2];
+    v[3] = SFB_SQRT2 * t[1][2]; v[4] = SFB_SQRT2 * t[0][2]; v[5] = SFB_SQRT2 * t[0][1];
+}
+__device__ __forceinline__ void vec_to_mat(const double v[6], double t[3][3]) {
+    t[0][0] = v[0]; t[1][1] = v[1]; t[2][2] = v[2];
+    t[0][1] = t[1][0] = v[5] / SFB_SQRT2; t[0][2] = t[2][0] = v[4] / SFB_SQRT2; t[1][2] = t[2][1] = v[3] / SFB_SQRT2;
+}
+__device__ __forceinline__ double dinner22(const double A[3][3], const double B[3][3]) {   // A_ij B_ji
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r += A[i][j] * B[j][i];
+        s += r;
+    }
+    return s;
+}
+
+// unblocked left-looking Cholesky of the LOWER triangle (LAPACK dpotf2 'L' semantics, which is what
+// dposv of the reference's LAPACK leaves behind on failure: failed pivot stored, info = column)
+__device__ __forceinline__ int potf2_lower(double a[6][6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double ajj = a[j][j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < j) ajj -= a[j][k] * a[j][k];
+        if (!(ajj > 0.0)) { a[j][j] = ajj; return j + 1; }
+        ajj = sqrt(ajj);
+        a[j][j] = ajj;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (i > j) {
+            double s = a[i][j];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (k < j) s -= a[i][k] * a[j][k];
+            a[i][j] = s / ajj;
+        }
+    }
+    return 0;
+}
+__device__ __forceinline__ void potrs_lower(const double a[6][6], double x[6]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = x[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < i) s -= a[i][k] * x[k];
+        x[i] = s / a[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = x[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k > i) s -= a[k][i] * x[k];
+        x[i] = s / a[i][i];
+    }
+}
+
+// Eij = (E11,E22,E33,E23,E13,E12) w.r.t. the rows of e[3][3].  returns status flags.
+__device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3], const double2 n4[5],
+                                                 const double e[3][3], const EijCoef& K, double E[6]) {
+    double a2v[6], a4p[21];
+    ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
+    ev_c4_mandel(n00, n2, n4, a4p);
+    double a2m[3][3];
+    vec_to_mat(a2v, a2m);
+    // ---- Taylor matrix P (src/homogenizations.f90:165-170) and its Cholesky factor
+    double P[6][6];
+    {
+        const double s = SFB_SQRT2;
+        const double Lm[6][6] = {
+            {2 * a2m[0][0], 0.0, 0.0, 0.0, s * a2m[0][2], s * a2m[0][1]},
+            {0.0, 2 * a2m[1][1], 0.0, s * a2m[1][2], 0.0, s * a2m[0][1]},
+            {0.0, 0.0, 2 * a2m[2][2], s * a2m[1][2], s * a2m[0][2], 0.0},
+            {0.0, s * a2m[1][2], s * a2m[1][2], a2m[1][1] + a2m[2][2], a2m[0][1], a2m[0][2]},
+            {s * a2m[0][2], 0.0, s * a2m[0][2], a2m[0][1], a2m[0][0] + a2m[2][2], a2m[1][2]},
+            {s * a2m[0][1], s * a2m[0][1], 0.0, a2m[0][2], a2m[1][2], a2m[0][0] + a2m[1][1]}};
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double idv = (i < 3) ? 1.0 : 0.0;
+                P[i][j] = ((i == j ? 1.0 : 0.0) - K.tA * (idv * a2v[j])) + K.tB * a4p[i <= j ? tri6(i, j) : tri6(j, i)] + K.tC * Lm[i][j];
+            }
+    }
+    int status = 0;
+    double F[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) F[i][j] = P[i][j];
+    const int info = potf2_lower(F);
+    double R[6][6];     // regularised normal matrix (only if the factorisation failed)
+    if (info != 0) {    // src/homogenizations.f90:177-185: P_reg = P^T P + 1e-6 I using the partially factorised P
+        status |= SFB_ST_TAYLOR_FALLBACK;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s += F[k][i] * F[k][j];
+                R[i][j] = s + (i == j ? 0x1.0c6f7ap-20 : 0.0);      // 1e-6 is a real(4) literal
+            }
+        if (potf2_lower(R) != 0) status |= SFB_ST_TAYLOR_FAILED;
+    }
+    bool finite = true;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        // (v,w) pairs: 11,22,33,23,13,12   src/enhancementfactors.f90:36-44
+        const int iv = (q < 3) ? q : (q == 3 ? 1 : 0);
+        const int iw = (q < 3) ? q : (q == 5 ? 1 : 2);
+        double tau[3][3], vw[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                vw[i][j] = e[iv][i] * e[iw][j];
+                if (q < 3) tau[i][j] = ((i == j) ? 1.0 / 3.0 : 0.0) - e[iv][i] * e[iv][j];   // tau_vv
+                else tau[i][j] = e[iv][i] * e[iw][j] + e[iw][i] * e[iv][j];                // tau_vw
+            }
+        double tv[6];
+        mat_to_vec(tau, tv);
+        // ---- Sachs (src/homogenizations.f90:88-91,115)
+        double a4t_v[6], a4t[3][3];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s += a4p[i <= j ? tri6(i, j) : tri6(j, i)] * tv[j];
+            a4t_v[i] = s;
+        }
+        vec_to_mat(a4t_v, a4t);
+        const double a2tau = dinner22(a2m, tau);
+        double eps[3][3], epsi[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double ac = 0.0;   // tau.a2 + a2.tau
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ac += tau[i][k] * a2m[k][j];
+                double ac2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ac2 += a2m[i][k] * tau[k][j];
+                eps[i][j] = ((1.0 * tau[i][j] - K.sA * a2tau * (i == j ? 1.0 : 0.0)) + K.sB * a4t[i][j]) + K.sC * (ac + ac2);
+                epsi[i][j] = K.s_iso * tau[i][j];
+            }
+        const double Es = dinner22(eps, vw) / dinner22(epsi, vw);
+        // ---- Taylor (src/homogenizations.f90:172-188)
+        double x[6];
+        if (info == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) x[i] = tv[i];
+            potrs_lower(F, x);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s += F[k][i] * tv[k];
+                x[i] = s;
+            }
+            potrs_lower(R, x);
+        }
+        double et[3][3], eti[3][3];
+        vec_to_mat(x, et);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) eti[i][j] = tau[i][j] / K.t_iso;
+        const double Et = dinner22(et, vw) / dinner22(eti, vw);
+        E[q] = (1 - K.alpha) * Es + K.alpha * Et;
+        finite = finite && isfinite(E[q]);
+    }
+    if (!finite) status |= SFB_ST_NONFINITE;
+    return status;
+}
+
+}  // namespace sfb

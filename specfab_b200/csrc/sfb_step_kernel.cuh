@@ -86,6 +86,8 @@ __device__ __forceinline__ void row_out(const Ctx& c, double kr, double ki, doub
     }
 }
 #define SFB_ROW_OUT(l, mu, ar, ai, zr, zi) row_out<l, mu>(c, ar, ai, zr, zi)
+// keeps the warps of a CTA within one instruction-cache window of the generated straight-line code
+#define SFB_LOCKSTEP() __syncthreads()
 
 __device__ __forceinline__ void apply_role(const Ctx& c, int role) {
     const double2* __restrict__ yz = c.yz;

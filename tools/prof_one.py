@@ -1,0 +1,20 @@
+"""Run a few launches of one step-kernel configuration (for ncu).  usage: prof_one.py L N terms scheme [steps]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import specfab_b200 as sf
+
+L, N, terms, scheme = int(sys.argv[1]), int(sys.argv[2]), tuple(sys.argv[3].split("+")), sys.argv[4]
+steps = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+lm, n = sf.init(L)
+g = torch.Generator(device="cuda").manual_seed(1)
+nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
+nlm[0] = 0.2820947917738781
+nlm[1:] = 1e-3 * torch.view_as_complex(torch.randn((n - 1, N, 2), dtype=torch.float64, device="cuda", generator=g))
+ug = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
+tau = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
+tau = (tau + tau.permute(1, 0, 2)) / 2
+out = torch.empty_like(nlm)
+for _ in range(steps):
+    sf.step_arr_dev(nlm, ug, tau, out=out, dt=1e-3, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
+torch.cuda.synchronize()

@@ -1,0 +1,53 @@
+"""Tuning aid: time every compiled kernel variant of (L, terms, scheme) and check it against variant 0."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import specfab_b200 as sf
+from specfab_b200 import _lib
+
+
+def run(L, N, terms, scheme, variants, steps=10):
+    lm, n = sf.init(L)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
+    nlm[0] = 0.2820947917738781
+    nlm[1:] = 1e-2 * torch.view_as_complex(torch.randn((n - 1, N, 2), dtype=torch.float64, device="cuda", generator=g))
+    ug = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
+    tau = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
+    tau = (tau + tau.permute(1, 0, 2)) / 2
+    kw = dict(dt=1e-3, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
+    ref = None
+    info = {(k["L"], k["ddrx"], k["variant"]): k for k in sf.build_info()["step_kernels"]}
+    for v in variants:
+        key = (L, int("ddrx" in terms), v)
+        if key not in info:
+            continue
+        _lib.load().sfb_set_variant(v)
+        out = torch.empty_like(nlm)
+        for _ in range(3):
+            sf.step_arr_dev(nlm, ug, tau, out=out, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sf.step_arr_dev(nlm, ug, tau, out=out, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if ref is None:
+            ref = out.clone()
+        err = float((out - ref).abs().max() / ref.abs().max())
+        k = info[key]
+        nst = 4 if scheme == "rk4" else 1
+        rate = N / (ms * 1e-3)
+        print(json.dumps(dict(L=L, terms="+".join(terms), scheme=scheme, variant=v, roles=k["roles"], tile=k["tile"], ms=round(ms, 4),
+                              rate=round(rate / 1e6, 1), tflops=round(2 * k["dfma_per_node_rhs"] * nst * rate / 1e12, 2), diff_vs_v0=err)), flush=True)
+    _lib.load().sfb_set_variant(0)
+
+
+if __name__ == "__main__":
+    V = list(range(0, 12))
+    run(8, 1_000_000, ("lrot", "reg"), "rk4", V)
+    run(8, 1_000_000, ("lrot", "reg"), "euler", V)
+    run(8, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
+    run(8, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
