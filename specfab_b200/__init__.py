@@ -87,11 +87,12 @@ def _farr(a, dtype, shape_tail):
 
 
 def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.0, Lambda=0.0,
-             terms=("lrot", "reg"), scheme="euler", nsteps=1):
+             terms=("lrot", "reg"), scheme="euler", nsteps=1, out=None):
     """Batched fused time step of N independent nodes (host arrays).
 
     nlm (N,nlm_len) complex128, ugrad (N,3,3), tau (N,3,3) or None (tau := sym(ugrad)).
-    Gamma0 / Lambda: scalars or (N,) arrays.  Returns the new nlm (N,nlm_len), Fortran-ordered.
+    Gamma0 / Lambda: scalars or (N,) arrays.  Returns the new nlm (N,nlm_len), Fortran-ordered
+    (written into `out` when given: a Fortran-ordered (N,nlm_len) complex128 array, e.g. pinned memory).
     Batches  nlm + dt*matmul(M_LROT + Gamma0*M_DDRX + Lambda*M_CDRX + M_REG, nlm)
     (reference per node: src/specfabpy/integrator.py:73-77, src/dynamics.f90:99-110)."""
     n = _need_init()
@@ -117,7 +118,10 @@ def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.
 
     o = _opts(dt, iota, zeta, nu, 0.0 if np.ndim(Gamma0) else Gamma0, 0.0 if np.ndim(Lambda) else Lambda,
               terms, scheme, nsteps, vec(Gamma0), vec(Lambda))
-    out = np.empty((N, n), dtype=np.complex128, order="F")
+    if out is None:
+        out = np.empty((N, n), dtype=np.complex128, order="F")
+    elif out.shape != (N, n) or out.dtype != np.complex128 or not out.flags.f_contiguous:
+        raise ValueError("out must be a Fortran-ordered complex128 array of shape (N, nlm_len)")
     _lib.check(lib.sfb_step_arr(nlm_f.ctypes.data, out.ctypes.data, N, N, ug.ctypes.data,
                                 ta.ctypes.data if ta is not None else None, C.byref(o)))
     return out

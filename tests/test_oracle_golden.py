@@ -1,0 +1,131 @@
+"""CPU: pins of the oracle.  The golden file holds outputs of the REFERENCE'S OWN
+formula text interpreted with Fortran kind semantics (tools/make_golden.py); the oracle's hand
+restatement must reproduce them to rounding."""
+import os
+
+import numpy as np
+
+import specfab_oracle as o
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "refbodies.npz"))
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(b).max()
+
+
+def test_generated_bodies_match_reference_text():
+    for c in range(G["nlm"].shape[0]):
+        nlm = G["nlm"][c]
+        n00, n2m, n4m = o.decompose_nlm(nlm)
+        c0 = o.f_ev_c0(n00)
+        assert rel(o.f_ev_c4(n00, n2m, n4m), G["a4_ev"][c] * G["a4_k"][c] / c0) < 1e-15       # ev_c4__body.f90 (real(4))
+        assert rel(o.f_ev_c4_Mandel(n00, n2m, n4m), G["a4M_ev"][c] * G["a4M_k"][c] / c0) < 1e-15  # ev_c4_Mandel__body.f90
+        assert rel(o.f_ev_c2(n00, n2m), np.sqrt(2 / 15.0) * G["c2_ev"][c] + np.eye(3) / 3) < 1e-15  # ev_c2__body.f90
+        assert rel(np.array(o.quad_rr(G["sym"][c])), G["quad_rr"][c]) < 1e-15                 # dynamics.f90:571-577
+        assert rel(np.array(o.quad_tp(G["skew"][c])), G["quad_tp"][c]) < 1e-15                # dynamics.f90:592
+        assert rel(np.array(o.lrot_weights(G["sym"][c], G["skew"][c], 1.0, 0.0)), G["lrot_g"][c]) < 1e-15  # dynamics.f90:78-91
+        k, g = o.ddrx_weights_raw(list(G["quad_rr"][c]))
+        assert k == G["ddrx_k"][c] and rel(g, G["ddrx_g"][c]) < 5e-16                          # ddrx-coupling-weights.f90
+
+
+def test_a4_reference_alias_quirk_is_in_the_golden_data():
+    """src/include/ev_c4__body.f90:78 assigns ev(3,2,1,2)=ev(1,2,3,3): the reference's a4 is not fully symmetric."""
+    ev = G["a4_ev"][0]
+    assert ev[2, 1, 0, 1] == ev[0, 1, 2, 2] and ev[2, 1, 0, 1] != ev[0, 1, 1, 2]
+
+
+def test_real4_constants():
+    """SURVEY.md A.1 table"""
+    assert o.SQRT3_F == 1.7320507764816284 and o.SQRT56_F == 0.9128709435462952
+    assert o.SQRT23_F == 0.8164966106414795 and o.SQRT32_F == 1.2247449159622192
+    assert o.TWOTHIRDS_F == 0.6666666865348816 and o.SQRT2_F == 1.4142135381698608
+    assert 6.0 / o.SQRT6_F == 2.449489653641921 and o.TIKHONOV_F == 9.999999974752427e-07
+    assert o.load_tables()["GC"][0, 0, 0] == 0.2820949852466583
+
+
+def test_isotropic_and_trace_pins():
+    L = 8
+    lm, n = o.init(L)
+    assert n == 45 and tuple(lm[:, 6]) == (4, -4)
+    iso = np.zeros(n, complex); iso[0] = 1 / np.sqrt(4 * np.pi)
+    assert np.array_equal(o.a2(iso), np.eye(3) / 3)
+    a4iso = np.zeros((3, 3, 3, 3))
+    I = np.eye(3)
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                for l in range(3):
+                    a4iso[i, j, k, l] = (I[i, j] * I[k, l] + I[i, k] * I[j, l] + I[i, l] * I[j, k]) / 15
+    assert 1e-10 < np.abs(o.a4(iso) - a4iso).max() < 1e-7      # only ~1e-8: real(4) constants
+    e = np.eye(3)
+    assert np.abs(o.Eij_tranisotropic(iso, e[0], e[1], e[2], (1, 1e3), 0.0125, 1) - 1).max() < 1e-12
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    assert abs(np.trace(o.a2(x)) - 1) < 1e-14
+
+
+def test_single_maximum_enhancement_pin():
+    """delta function, ice 'linear' -> E_mt = 9.97 ('=10'), E_mm = 0.00997"""
+    o.init(8)
+    d = np.zeros(45, complex)
+    d[0] = 1 / np.sqrt(4 * np.pi); d[3] = np.sqrt(5 / (4 * np.pi)); d[10] = 3 / np.sqrt(4 * np.pi)
+    e = np.eye(3)
+    E = o.Eij_tranisotropic(d, e[0], e[1], e[2], (1, 1e3), 0.0125, 1)
+    assert np.allclose(E, [9.97005242e-3] * 3 + [9.97005242, 9.97005242, 9.97005242e-3], rtol=1e-8)
+
+
+def test_fabdyn_lrot_scenario_and_row0_residual():
+    """docs/snippets/fabdyn-LROT.py scenario + the ~1e-6 first-row residual of M_LROT"""
+    o.init(8)
+    ug = np.diag([.5, .5, -1.])
+    M = o.M_LROT(ug, np.zeros((3, 3)), 1.0, 0.0)
+    assert abs(np.abs(M[0]).max() - 1.4436e-6) < 1e-9 and np.count_nonzero(M) == 100 and np.abs(M.imag).max() == 0
+    x = np.zeros(45, complex); x[0] = 1 / np.sqrt(4 * np.pi)
+    for _ in range(25):
+        x = o.step_euler(x, 0.05, ug, use_reg=False)
+    assert np.allclose(np.diag(o.a2(x)), [0.09693296, 0.09693296, 0.80613408], atol=1e-8)
+    assert abs(x[3].real / x[0].real - 1.5858219082588) < 1e-12 and abs(x[10].real / x[0].real - 1.5872145434530) < 1e-12
+
+
+def test_fabdyn_ddrx_scenario():
+    o.init(8)
+    S = np.diag([.5, .5, -1.])
+    x = np.zeros(45, complex); x[0] = 1 / np.sqrt(4 * np.pi)
+    assert o.ev_D2(x, S) == 0.9999999999999997
+    n00 = x[0].real
+    for _ in range(24):
+        x = x + 0.05 * ((10 * o.M_DDRX(x, S)) @ x)
+    assert np.allclose(np.diag(o.a2(x)), [0.26002527, 0.26002527, 0.47994946], atol=1e-8)
+    assert abs(o.ev_D2(x, S) - 1.75353373) < 1e-8 and abs(x[0].real / n00 - 1 - 1.435e-5) < 1e-8
+
+
+def test_lrot_preserves_reality_symmetry():
+    """tests/reduced-form/reduced-form.f90 -- n_l^-m = (-1)^m conj(n_l^m) is preserved"""
+    L = 8
+    lm, n = o.init(L)
+    rng = np.random.default_rng(0)
+    ug = rng.standard_normal((3, 3)); ug -= np.eye(3) * np.trace(ug) / 3
+    x = np.zeros(n, complex); x[0] = 1 / np.sqrt(4 * np.pi)
+    for _ in range(50):
+        x = o.step_euler(x, 0.02, ug)
+    idx = {(int(l), int(m)): j for j, (l, m) in enumerate(zip(lm[0], lm[1]))}
+    err = max(abs(x[idx[(l, -m)]] - (-1) ** abs(m) * np.conj(x[idx[(l, m)]])) for (l, m) in idx)
+    assert err < 1e-15 and abs(np.trace(o.a2(x)) - 1) < 1e-14
+
+
+def test_regularisation_and_cdrx_diagonals():
+    o.init(12)
+    D = np.diag([.5, .5, -1.])
+    M = o.M_REG(D)
+    assert np.count_nonzero(M - np.diag(np.diag(M))) == 0
+    assert abs(M[-1, -1] + 10.6068117205577668 * np.sqrt(1.5)) < 1e-13       # l = L mode: -nu*||D||
+    assert np.array_equal(np.diag(o.M_CDRX())[:6], [0, -6, -6, -6, -6, -6])
+
+
+def test_apply_bounds():
+    o.init(8)
+    x = np.zeros(45, complex); x[0] = 1 / np.sqrt(4 * np.pi)
+    x[3] = 5.0
+    y = o.apply_bounds(x)
+    assert abs(o.Sl(y, 2) / x[0].real ** 2 - 1) < 1e-14 and np.array_equal(y[6:], x[6:])
