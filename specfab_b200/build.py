@@ -30,22 +30,32 @@ ALL_L = [4, 6, 8, 10, 12, 14, 16, 18, 20]
 # tuning table: (L, ddrx) -> (roles R, tile nodes TN, min CTAs/SM for __launch_bounds__)
 # variant 0 is the default; extra variants (EXTRA) are selectable with sfb_set_variant() for tuning runs
 EXTRA = {
-    # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]
-    (8, 0): [(1, 2, 32, 2, "imm", False), (2, 1, 64, 1, "cbank", True), (4, 2, 64, 1, "cbank", True)],
-    (8, 1): [(1, 2, 32, 2, "imm", False), (2, 1, 64, 1, "cbank", True), (4, 2, 64, 1, "cbank", True)],
+    # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]   R = 0 selects the four-lane kernel
+    (8, 1): [(1, 1, 16, 6, "imm", False), (2, 1, 32, 3, "imm", False), (10, 0, 64, 2, "imm", True), (11, 0, 32, 4, "imm", True),
+             (12, 0, 16, 6, "imm", True), (13, 0, 128, 1, "imm", True)],
+    (12, 0): [(1, 1, 16, 4, "imm", False), (2, 1, 32, 2, "imm", False), (10, 0, 16, 4, "imm+w", True), (11, 0, 32, 2, "imm+w", True),
+              (12, 0, 8, 6, "imm+w", True)],
+    (12, 1): [(1, 1, 16, 4, "imm", False), (2, 2, 16, 3, "imm", False), (10, 0, 16, 4, "imm", True), (11, 0, 32, 2, "imm", True),
+              (12, 0, 8, 6, "imm", True), (13, 0, 64, 1, "imm", True)],
+    (20, 0): [(1, 1, 16, 3, "imm", False), (2, 2, 16, 3, "imm", False), (10, 0, 16, 3, "imm", True), (11, 0, 8, 6, "imm", True),
+              (12, 0, 32, 1, "imm", True)],
+    (20, 1): [(1, 1, 16, 2, "imm", False), (2, 2, 16, 2, "imm", False), (10, 0, 16, 2, "imm", True), (11, 0, 8, 5, "imm", True),
+              (12, 0, 32, 1, "imm", True)],
+    (4, 0): [(1, 1, 32, 8, "imm", False), (10, 0, 16, 8, "imm+w", True)],
+    (4, 1): [(1, 1, 32, 8, "imm", False), (10, 0, 16, 8, "imm", True), (11, 0, 64, 2, "imm", True)],
 }
-# default variant: single instruction stream per CTA (R = 1) kept in lockstep -- ncu showed the
-# multi-role / multi-CTA layouts stall on instruction fetch (profiles/r01_notes.md)
+# default variant (0).  ncu (profiles/r01_notes.md): small tiles with several independent CTAs per SM hide the
+# per-tile load / prep phases; the DDRX kernels prefer four lanes per node (more threads per resident node).
 TUNE = {
-    (4, 0): (1, 64, 1, "imm", True), (4, 1): (1, 64, 1, "imm", True),
-    (6, 0): (1, 64, 1, "imm", True), (6, 1): (1, 64, 1, "imm", True),
-    (8, 0): (1, 64, 1, "imm", True), (8, 1): (1, 64, 1, "imm", True),
-    (10, 0): (1, 32, 1, "imm", True), (10, 1): (2, 32, 1, "imm", True),
-    (12, 0): (1, 32, 1, "imm", True), (12, 1): (2, 32, 1, "imm", True),
-    (14, 0): (2, 16, 1, "imm", True), (14, 1): (4, 16, 1, "imm", True),
-    (16, 0): (4, 16, 1, "imm", True), (16, 1): (4, 16, 1, "imm", True),
-    (18, 0): (4, 16, 1, "imm", True), (18, 1): (4, 16, 1, "imm", True),
-    (20, 0): (4, 16, 1, "imm", True), (20, 1): (4, 16, 1, "imm", True),
+    (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
+    (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
+    (8, 0): (1, 16, 6, "imm", False), (8, 1): (0, 64, 2, "imm", True),
+    (10, 0): (0, 16, 4, "imm+w", True), (10, 1): (0, 32, 2, "imm", True),
+    (12, 0): (0, 16, 4, "imm+w", True), (12, 1): (0, 32, 2, "imm", True),
+    (14, 0): (2, 16, 3, "imm", False), (14, 1): (2, 16, 2, "imm", False),
+    (16, 0): (2, 16, 3, "imm", False), (16, 1): (2, 16, 2, "imm", False),
+    (18, 0): (2, 16, 3, "imm", False), (18, 1): (2, 16, 2, "imm", False),
+    (20, 0): (2, 16, 3, "imm", False), (20, 1): (2, 16, 2, "imm", False),
 }
 
 
@@ -68,11 +78,23 @@ def generate(Ls):
             variants = [(0, R, TN, MINB, cm0, sy0)] + (EXTRA.get((L, dd), []) if os.environ.get("SFB_EXTRA_VARIANTS", "1") == "1" else [])
             for (vid, R, TN, MINB, cmode, sync) in variants:
                 tag = "L%d_%s" % (L, "ddrx" if dd else "lrot") + ("_v%d" % vid if vid else "")
-                body, tab, meta = emit_step.emit(L, dd, R, TN, cmode, sync)
+                # const_mode string: "imm" | "cbank", optional flags "+w" (register window), "+cN" (>= N DFMA
+                # chains per lane), "+gN" (lock-step barrier every >= N DFMAs)
+                parts = cmode.split("+")
+                cm = parts[0]
+                window = "w" in parts[1:]
+                mc = max([int(x[1:]) for x in parts[1:] if x.startswith("c")] + [1])
+                gd = max([int(x[1:]) for x in parts[1:] if x.startswith("g")] + [0])
+                if R == 0:
+                    body, tab, meta = emit_step.emit4(L, dd, TN, cm, sync, window, mc, gd)
+                    skeleton = "sfb_step_kernel4.cuh"
+                else:
+                    body, tab, meta = emit_step.emit(L, dd, R, TN, cm, sync, mc, gd)
+                    skeleton = "sfb_step_kernel.cuh"
                 _write_if_changed(os.path.join(GEN, "apply_%s.inc" % tag), body)
                 cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_R %d\n#define SFB_TN %d\n#define SFB_MINB %d\n'
                       '#define SFB_NAME sfb_launch_step_%s\n#define SFB_APPLY_INC "gen/apply_%s.inc"\n%s'
-                      '#include "sfb_step_kernel.cuh"\n' % (L, dd, R, TN, MINB, tag, tag, tab))
+                      '#include "%s"\n' % (L, dd, R, TN, MINB, tag, tag, tab, skeleton))
                 path = os.path.join(GEN, "step_%s.cu" % tag)
                 _write_if_changed(path, cu)
                 units.append(path)

@@ -22,6 +22,7 @@ struct SfbStepParams {
     double dt, iota, zeta, nu_mult, gamma0, lambda;
     int nstage;              // 1 = Euler, 4 = classical RK4
     int use_lrot, use_reg;
+    const double2* ktab;     // set by the launcher in gtab mode
     int n0_global;           // set by the launcher: RK4 re-reads n0 from global (3 smem buffers)
 };
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
 
 // a2 as Mandel 6-vector.  n2: n_2^m for m = 0,1,2 (only m>=0 enters, ev_c2__body.f90:1-17)
 __device__ __forceinline__ void ev_c2_mandel(double2 n00, double2 n20, double2 n21, double2 n22, double a2v[6]) {
-    const double2 h0 = cdiv(n20, n00), h1 = cdiv(n21, n00), h2 = cdiv(n22, n00);
+    const double2 h0 = cdiv(n20, n00), h1 = cdiv(n21, n00), h2 = cdiv(n22, n00);   // n2mhat = n2m/n00
     const double c = 0.5 * 0.816496580927726;      // 0.5d0*sqrt(2.0d0/3)
     const double s215 = 0.3651483716701107;        // sqrt(2/15.0d0)
     const double third = 1.0 / 3.0;
@@ -77,8 +77,9 @@ __device__ __forceinline__ void ev_c4_mandel(double2 n00, const double2 n2[3], c
     e[tri6(5, 5)] = 2.0 * (7.0 * r00 + (-2.0 * s5) * r20 + r40 + (-1.0 * s70) * r44);
     const double k = 0x1.149200acaee94p-5;       // (2*Sqrt(Pi))/105. = 0.03376102573153364
     const double c0 = 3.5449077018110318 * r00;  // f_ev_c0 = REAL(sqrt(4*Pi)*n00)  src/moments.f90:184-189
+    const double kc = k / c0;                    // ev*k/f_ev_c0: one division instead of 21 (differs by <= 1 ulp)
 #pragma unroll
-    for (int q = 0; q < 21; ++q) e[q] = e[q] * k / c0;
+    for (int q = 0; q < 21; ++q) e[q] = e[q] * kc;
 }
 
 // <D> = 5[(tau.tau):a2 - tau:a4:tau]/(tau:tau)       src/dynamics.f90:402-422

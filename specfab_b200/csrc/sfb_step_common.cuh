@@ -1,0 +1,195 @@
+// Device helpers shared by the step-kernel skeletons: quadric coefficients, DDRX weights and the
+// per-node forcing preparation.  Included INSIDE the anonymous namespace of a step translation unit,
+// after kTN, kNF, c_reg and the SC_* scalar slots are defined.
+// ---- complex helpers (forcing preparation) ----
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double2 cneg(double2 a) { return make_double2(-a.x, -a.y); }
+
+// src/dynamics.f90:563-579 ; q[0..4] <-> m = -2..2 ; M symmetric, row-major m[3][3]
+__device__ __forceinline__ void quad_rr(const double m[3][3], double2 q[5]) {
+    const double fsq = 0x1.4b5eee37a973cp-1;    // sqrt(2*Pi/15)
+    const double sp5 = 0x1.95d83f429fefap-1;    // sqrt(Pi/5)
+    const double xx = m[0][0], yy = m[1][1], zz = m[2][2], xy = m[0][1], xz = m[0][2], yz = m[1][2];
+    q[0] = make_double2(fsq * (xx - yy), fsq * (2 * xy));
+    q[1] = make_double2((2 * fsq) * xz, (2 * fsq) * yz);
+    q[2] = make_double2(-((SFB_TWOTHIRDS_F * sp5) * (xx + yy - 2 * zz)), 0.0);
+    q[3] = make_double2(-((2 * fsq) * xz), (2 * fsq) * yz);
+    q[4] = make_double2(fsq * (xx - yy), fsq * (-2 * xy));
+}
+
+// src/dynamics.f90:581-593 ; q[0..2] <-> m = -1..1 ; M antisymmetric
+__device__ __forceinline__ void quad_tp(const double m[3][3], double2 q[3]) {
+    const double fsq1 = 0x1.727bdd17583bbp+0;   // sqrt(2*Pi/3)
+    const double xy = m[0][1], xz = m[0][2], yz = m[1][2];
+    q[0] = make_double2(fsq1 * yz, fsq1 * (-xz));
+    q[1] = make_double2(fsq1 * (SFB_SQRT2_F * xy), 0.0);
+    q[2] = make_double2(fsq1 * (-yz), fsq1 * (-xz));
+}
+
+#if SFB_DDRX
+// src/include/ddrx-coupling-weights.f90:1-16 with real(4) constants; qt**(2.0) == qt*qt
+__device__ __forceinline__ void ddrx_weights_raw(const double2 qt[5], double2 g[15]) {
+    const double s5 = 0x1.1e377ap+1, s15 = 0x1.3988e2p+0, s6 = 0x1.3988e2p+1, s2 = 0x1.6a09e6p+0, s3 = 0x1.bb67aep+0;
+    const double c2s14 = 0x1.deeea2p+2;   // 2*Sqrt((14.0))   real(4)
+    const double c4s7 = 0x1.52a7fap+3;    // 4*Sqrt((7.0))    real(4)
+    const double c3s5 = 0x1.ad5338p+2;    // 3.*Sqrt((5.0))   real(4)
+    const double2 qm2 = qt[0], qm1 = qt[1], q0 = qt[2], qp1 = qt[3], qp2 = qt[4];
+    const double2 q0q0 = cmul(q0, q0), qm1qm1 = cmul(qm1, qm1), qp1qp1 = cmul(qp1, qp1);
+    double2 t;
+    t = cadd(cadd(q0q0, cmul(cscale(-2.0, qm1), qp1)), cmul(cscale(2.0, qm2), qp2));
+    t = cscale(7.0, t); g[0] = make_double2(t.x / s5, t.y / s5);
+    g[1] = cadd(cscale(s15, qm1qm1), cmul(cscale(-2.0, q0), qm2));
+    g[2] = cadd(cmul(q0, qm1), cmul(cscale(-s6, qp1), qm2));
+    g[3] = cadd(cadd(q0q0, cmul(cscale(-1.0, qm1), qp1)), cmul(cscale(-2.0, qm2), qp2));
+    g[4] = cadd(cmul(q0, qp1), cmul(cscale(-s6, qm1), qp2));
+    g[5] = cadd(cscale(s15, qp1qp1), cmul(cscale(-2.0, q0), qp2));
+    t = cneg(cscale(c2s14, cmul(qm2, qm2))); g[6] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cmul(cscale(c4s7, qm1), qm2)); g[7] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cscale(4.0, cadd(cscale(s2, qm1qm1), cmul(cscale(s3, q0), qm2)))); g[8] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cscale(4.0, cadd(cmul(cscale(s6, q0), qm1), cmul(qp1, qm2)))); g[9] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cscale(4.0, cadd(cadd(cscale(3.0, q0q0), cmul(cscale(4.0, qm1), qp1)), cmul(qm2, qp2))));
+    g[10] = make_double2(t.x / c3s5, t.y / c3s5);
+    t = cneg(cscale(4.0, cadd(cmul(cscale(s6, q0), qp1), cmul(qm1, qp2)))); g[11] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cscale(4.0, cadd(cscale(s2, qp1qp1), cmul(cscale(s3, q0), qp2)))); g[12] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cmul(cscale(c4s7, qp1), qp2)); g[13] = make_double2(t.x / 3.0, t.y / 3.0);
+    t = cneg(cscale(c2s14, cmul(qp2, qp2))); g[14] = make_double2(t.x / 3.0, t.y / 3.0);
+}
+#endif
+
+// catalyst index k of (lk,mk) and of its mirror (lk,-mk); k = 0 | 1..5 | 6..14
+__device__ __forceinline__ int cat_mirror(int k) { return k == 0 ? 0 : (k < 6 ? 6 - k + 0 : 20 - k); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------------------------------------
+// Per-node forcing preparation, split into independent tasks so that the threads of a CTA share it
+// (task = tid / kTN is warp uniform for kTN >= 32):
+//   task 0: M_LROT weights + M_REG / M_CDRX scalars      task 1: DDRX weights g      task 2: <D> ingredients
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_sym_skew(const SfbStepParams& P, long long node, double D[3][3], double W[3][3]) {
+    double u[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) u[i][j] = P.ugrad[(long long)(i + 3 * j) * P.ld_u + node];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { D[i][j] = (u[i][j] + u[j][i]) / 2; W[i][j] = (u[i][j] - u[j][i]) / 2; }
+}
+
+__device__ __forceinline__ void load_tau(const SfbStepParams& P, long long node, double T[3][3]) {
+    if (P.tau) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) T[i][j] = P.tau[(long long)(i + 3 * j) * P.ld_t + node];
+    } else {   // tau := D (src/specfabpy/integrator.py:39)
+        double W[3][3];
+        load_sym_skew(P, node, T, W);
+    }
+}
+
+__device__ void prep_lrot(const SfbStepParams& P, long long node, int t, double2* forc, double* scal) {
+    double D[3][3], W[3][3];
+    load_sym_skew(P, node, D, W);
+    double2* fA = forc + t;                    // lane set A block: entry e at fA[e*kTN]
+    double2* fB = forc + kNF * kTN + t;        // lane set B block
+    // ---- M_LROT weights, src/dynamics.f90:71-76
+    double sq[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sq[i][j] = D[i][0] * D[0][j] + D[i][1] * D[1][j] + D[i][2] * D[2][j];
+    const double zetanorm = P.zeta / sqrt(sq[0][0] + sq[1][1] + sq[2][2]);   // 0/0 -> NaN like the reference
+    double E[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) E[i][j] = P.iota * D[i][j] + zetanorm * sq[i][j];
+    double2 qe[5], qo[3];
+    quad_rr(E, qe);
+    quad_tp(W, qo);
+    if (!P.use_lrot) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) qe[i] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) qo[i] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) { fA[(d + 2) * kTN] = qe[d + 2]; fB[(d + 2) * kTN] = qe[-d + 2]; }
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+        fA[(5 + d + 1) * kTN] = make_double2(-qo[d + 1].y, qo[d + 1].x);        //  i*qo[d]
+        fB[(5 + d + 1) * kTN] = make_double2(qo[-d + 1].y, -qo[-d + 1].x);      // -i*qo[-d]
+    }
+    // M_REG: -nu*||D||_F * regdiag   src/dynamics.f90:516-517
+    double fro = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) fro += D[i][j] * D[i][j];
+    scal[SC_RM * kTN + t] = P.use_reg ? -(P.nu_mult * (c_reg.nu * sqrt(fro))) : 0.0;
+    scal[SC_LAM * kTN + t] = P.lambda_arr ? P.lambda_arr[node] : P.lambda;
+    scal[SC_C0 * kTN + t] = 0.0;
+}
+
+#if SFB_DDRX
+__device__ void prep_ddrx_g(const SfbStepParams& P, long long node, int t, double2* forc, double* scal) {
+    double2* fA = forc + t;
+    double2* fB = forc + kNF * kTN + t;
+    const double g0 = P.gamma0_arr ? P.gamma0_arr[node] : P.gamma0;
+    scal[SC_G0 * kTN + t] = g0;
+    double T[3][3];
+    load_tau(P, node, T);
+    double2 qt[5], g[15];
+    quad_rr(T, qt);
+    ddrx_weights_raw(qt, g);
+    double dd = 0.0;                                   // doubleinner22(tau,tau) = tau_ij tau_ji
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dd += T[i][j] * T[j][i];
+    const double kk = 0x1.14d2dcd9ceb17p-3;            // (3*Sqrt(5/Pi))/28.
+    // g = k*g*5/(tau:tau) (src/dynamics.f90:293), then *Gamma0: one division per node instead of 30
+    const double sc = g0 * ((kk * 5) / dd);
+#pragma unroll
+    for (int k = 0; k < 15; ++k) g[k] = make_double2(sc * g[k].x, sc * g[k].y);
+#pragma unroll
+    for (int k = 0; k < 15; ++k) { fA[(8 + k) * kTN] = g[k]; fB[(8 + k) * kTN] = g[cat_mirror(k)]; }
+}
+
+__device__ void prep_ddrx_d(const SfbStepParams& P, long long node, int t, double* scal) {
+    // <D> ingredients, src/dynamics.f90:415-417
+    double T[3][3];
+    load_tau(P, node, T);
+    double sq[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sq[i][j] = T[i][0] * T[0][j] + T[i][1] * T[1][j] + T[i][2] * T[2][j];
+    const double tv[6] = {T[0][0], T[1][1], T[2][2], SFB_SQRT2 * T[1][2], SFB_SQRT2 * T[0][2], SFB_SQRT2 * T[0][1]};
+    const double sv[6] = {sq[0][0], sq[1][1], sq[2][2], SFB_SQRT2 * sq[1][2], SFB_SQRT2 * sq[0][2], SFB_SQRT2 * sq[0][1]};
+#pragma unroll
+    for (int p = 0; p < 6; ++p) { scal[(SC_TAUV + p) * kTN + t] = tv[p]; scal[(SC_TSQV + p) * kTN + t] = sv[p]; }
+    scal[SC_NORM * kTN + t] = sq[0][0] + sq[1][1] + sq[2][2];
+}
+#endif
+
+// task dispatch: kThreads >= 2*kTN in both skeletons
+__device__ __forceinline__ void prep_tile(const SfbStepParams& P, long long node0, int nvalid, int tid, double2* forc, double* scal) {
+    const int task = tid / kTN, t = tid - task * kTN;
+    if (t >= nvalid) return;
+    if (task == 0) prep_lrot(P, node0 + t, t, forc, scal);
+#if SFB_DDRX
+    if (kThreads >= 3 * kTN) {
+        if (task == 1) prep_ddrx_g(P, node0 + t, t, forc, scal);
+        if (task == 2) prep_ddrx_d(P, node0 + t, t, scal);
+    } else if (task == 1) {
+        prep_ddrx_g(P, node0 + t, t, forc, scal);
+        prep_ddrx_d(P, node0 + t, t, scal);
+    }
+#endif
+}

@@ -1,18 +1,18 @@
-// Fused fabric-evolution step kernel (sm_100a), one translation unit per (L, term set).
+// Fused fabric-evolution step kernel, FOUR lanes per node (sm_100a), one translation unit per (L, term set).
 //
-// Computes, for a tile of SFB_TN nodes per CTA,  nlm <- step(nlm)  with
-//     d nlm/dt = (M_LROT + Gamma0*M_DDRX + Lambda*M_CDRX + M_REG) nlm
-// (reference: src/dynamics.f90:52-97, 251-298, 402-422, 474-518; Euler update src/dynamics.f90:108;
-//  classical RK4 per BASELINE config 2) without ever forming M:
-//   * the tile's state is staged once in shared memory by 1-D TMA bulk copies (one per coefficient
-//     row, rows are node-contiguous) and stays there for all RK stages;
-//   * every node is served by 2*SFB_R lanes: lane set A (rows m>=0) / B (rows m<=0) of SFB_R warp
-//     roles; A and B run the same generated instruction stream (mirror symmetry of the Gaunt
-//     tables, see codegen/operators.py), roles split the canonical m's;
-//   * table entries are immediates of the generated straight-line code (codegen/emit_step.py).
+//   d nlm/dt = (M_LROT + Gamma0*M_DDRX + Lambda*M_CDRX + M_REG) nlm      Euler / classical RK4
+//   (reference: src/dynamics.f90:52-97, 251-298, 402-422, 474-518, 108; RK4 per BASELINE config 2)
+//
+// Work decomposition (see codegen/emit_step.py, emit4): a node is served by the lanes
+//   (sign set A: rows m>=0 | B: rows m<=0)  x  (component: re | im)
+// which all execute ONE generated straight-line instruction stream; a warp holds 8 nodes, a CTA
+// SFB_TN nodes = SFB_TN/8 warps kept in lock step (one instruction-cache window for the whole SM:
+// profiles/r01_notes.md).  The tile's state lives in shared memory for all RK stages (1-D TMA bulk
+// loads, one per coefficient row); every state value is read from shared memory once per stage and
+// kept in registers across the canonical-m sweep; table entries are immediates.
 //
 // Included by generated .cu files that define:
-//   SFB_L, SFB_DDRX (0/1), SFB_R, SFB_TN, SFB_MINB, SFB_NAME (launcher symbol), SFB_APPLY_INC
+//   SFB_L, SFB_DDRX (0/1), SFB_TN, SFB_MINB, SFB_NAME (launcher symbol), SFB_APPLY_INC
 #pragma once
 #include <cstring>
 #include "sfb_common.cuh"
@@ -22,88 +22,92 @@ namespace {
 
 constexpr int kL = SFB_L;
 constexpr int kNCoef = (kL + 1) * (kL + 2) / 2;
-constexpr int kNRow = 2 * (kL / 2 + 1) * (kL / 2 + 1);   // physical rows: 2 planes (m>=0 | m<0) per (l,|m|) slot
+constexpr int kNRow = 2 * (kL / 2 + 1) * (kL / 2 + 1);   // physical rows: plane pair (m>=0 | m<0) per (l,|m|) slot
 constexpr int kTN = SFB_TN;
-constexpr int kR = SFB_R;
-constexpr int kG = kTN / 16;
-constexpr int kThreads = 32 * kG * kR;
+constexpr int kThreads = 4 * kTN;
 constexpr int kNF = SFB_DDRX ? 23 : 8;                    // forcing entries per lane set
 constexpr int kNSc = SFB_DDRX ? 17 : 4;                   // per-node scalars
-static_assert(kTN % 16 == 0, "tile must be a multiple of 16 nodes");
+static_assert(kTN % 8 == 0, "tile must be a multiple of 8 nodes (one warp)");
 
 __constant__ SfbRegConst c_reg;
 
 __host__ __device__ constexpr int pslot(int l, int a) { return (l / 2) * (l / 2) + a; }
 __host__ __device__ constexpr int hrow(int l) { return l * (l + 1) / 2; }
 
-// scalar slots
 enum { SC_C0 = 0, SC_LAM = 1, SC_RM = 2, SC_G0 = 3, SC_TAUV = 4, SC_TSQV = 10, SC_NORM = 16 };
 
 struct Ctx {
-    const double2 *yz, *yp, *yn;      // stage input planes (zero / positive / negative canonical m)
+    const double *yz, *yp, *yn;       // stage input planes for this lane's component (zero / pos / neg canonical m)
     const double2* ktab;              // global table of operator entries (gtab mode)
-    const double2* fz;                // forcing block of this lane set
-    double2 *oz, *op;                 // next-stage buffer (rows owned by this lane: zero / positive plane)
-    double2 *az, *ap;                 // RK accumulator buffer
-    double2* gout;                    // global output, already offset by node
-    const double2* gin;               // global input (n0 re-read when the 4th smem buffer does not fit)
-    long long ld_out, sld;            // row stride, signed row stride (+ld for set A, -ld for set B)
-    long long ld_in, sld_in;
+    const double2* fz;                // forcing block of this lane's sign set
+    double *oz, *op;                  // next-stage buffer (rows owned by this lane)
+    double *az, *ap;                  // RK accumulator buffer
+    double* gout;                     // global output: component of node, row stride 2*ld doubles
+    const double* gin;                // global input (n0 re-read in RK stages 2,3)
+    long long ld_out, sld, ld_in, sld_in;
     double c0, lam, rm;               // diagonal: c0 + lam*(-l(l+1)) + rm*regdiag_l
-    double as, bs;                    // stage coefficients: ynext = n0 + as*k ; acc += bs*k
+    double as, bs;                    // ynext = n0 + as*k ; acc += bs*k
+    double sigma;                     // -1 (re lane) / +1 (im lane): sign of the partner's contribution
     bool first, last, isA, valid, ld_n0, ld_acc;
 };
 
-// RK4 formulation: see sfb_step_kernel4.cuh (Horner form of the Taylor polynomial for the linear,
-// DDRX-free kernels; classical k1..k4 with an accumulator buffer when DDRX makes the RHS state dependent).
+// RK4 formulation.  Kernels without DDRX are linear in nlm with stage-independent M, for which classical
+// RK4 equals the 4th-order Taylor polynomial; it is evaluated in Horner form
+//     y1 = n0 + dt/4 M n0 ; y2 = n0 + dt/3 M y1 ; y3 = n0 + dt/2 M y2 ; out = n0 + dt M y3
+// (2 state buffers, no accumulator; differs from the k1..k4 form only by roundings, ~1e-16).
+// DDRX kernels (<D> depends on the stage state) use the classical k1..k4 form with an accumulator buffer.
 #define SFB_HORNER (!SFB_DDRX)
 
 // loads issued at the START of a canonical-m block so that their latency overlaps the block's arithmetic
 template <int l, int mu>
-__device__ __forceinline__ double2 n0_load(const Ctx& c) {
-    double2 v = make_double2(0.0, 0.0);
-    if (c.ld_n0 && (mu != 0 || c.isA)) v = c.gin[(long long)hrow(l) * c.ld_in + (long long)mu * c.sld_in];
+__device__ __forceinline__ double n0_load(const Ctx& c) {
+    double v = 0.0;
+    if (c.ld_n0 && (mu != 0 || c.isA)) v = c.gin[2 * ((long long)hrow(l) * c.ld_in + (long long)mu * c.sld_in)];
     return v;
 }
 template <int l, int mu>
-__device__ __forceinline__ double2 acc_load(const Ctx& c) {
-    double2 v = make_double2(0.0, 0.0);
-#if !SFB_HORNER
-    if (c.ld_acc) v = (mu == 0 ? c.az : c.ap)[2 * pslot(l, mu) * kTN];
+__device__ __forceinline__ double acc_load(const Ctx& c) {
+#if SFB_HORNER
+    return 0.0;
+#else
+    double v = 0.0;
+    if (c.ld_acc) v = (mu == 0 ? c.az : c.ap)[4 * pslot(l, mu) * kTN];
+    return v;
 #endif
-    return v;
 }
-// finalize one row, branch-free (selects + predicated stores)
+// finalize one row (branch-free: selects + predicated stores): exchange the cross-component partial sum
+// with the partner lane, add the diagonal terms, apply the stage update for this lane's component
 template <int l, int mu>
-__device__ __forceinline__ void row_out(const Ctx& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
+__device__ __forceinline__ void row_out(const Ctx& c, double mine, double theirs, double z, double n0, double acc) {
+    const double recv = __shfl_xor_sync(0xffffffffu, theirs, 1);
+    double k = fma(c.sigma, recv, mine);
     double d = fma(c.lam, -(double)(l * (l + 1)), c.c0);
     d = fma(c.rm, c_reg.regdiag[l / 2], d);
-    kr = fma(d, zr, kr);
-    ki = fma(d, zi, ki);
-    constexpr int off = 2 * pslot(l, mu) * kTN;
-    const bool own = (mu != 0) || c.isA;             // m = 0 rows are computed by both lane sets; set A owns them
-    const double n0r = c.first ? zr : n0.x, n0i = c.first ? zi : n0.y;
-    const long long goff = (long long)hrow(l) * c.ld_out + (long long)mu * c.sld;
+    k = fma(d, z, k);
+    constexpr int off = 4 * pslot(l, mu) * kTN;      // doubles
+    const bool own = (mu != 0) || c.isA;             // m = 0 rows are computed by both sign sets; A owns them
+    const double n0v = c.first ? z : n0;
+    const long long goff = 2 * ((long long)hrow(l) * c.ld_out + (long long)mu * c.sld);
 #if SFB_HORNER
-    const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
+    const double y = fma(c.as, k, n0v);
     if (own && !c.last) (mu == 0 ? c.oz : c.op)[off] = y;
     if (own && c.last && c.valid) c.gout[goff] = y;
 #else
-    const double2 A = make_double2(fma(c.bs, kr, c.first ? zr : acc.x), fma(c.bs, ki, c.first ? zi : acc.y));
-    const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
+    const double A = fma(c.bs, k, c.first ? z : acc);
+    const double y = fma(c.as, k, n0v);
     if (own && !c.last) { (mu == 0 ? c.oz : c.op)[off] = y; (mu == 0 ? c.az : c.ap)[off] = A; }
     if (own && c.last && c.valid) c.gout[goff] = A;
 #endif
 }
-#define SFB_ROW_PRE(l, mu, q, r) const double2 q = n0_load<l, mu>(c), r = acc_load<l, mu>(c)
-#define SFB_ROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out<l, mu>(c, ar, ai, zr, zi, q, r)
-// keeps the warps of a CTA within one instruction-cache window of the generated straight-line code
+#define SFB_ROW_OUT4(l, mu, m, t, z, q, r) row_out<l, mu>(c, m, t, z, q, r)
+#define SFB_N0_LOAD(l, mu) n0_load<l, mu>(c)
+#define SFB_ACC_LOAD(l, mu) acc_load<l, mu>(c)
 #define SFB_LOCKSTEP() __syncthreads()
 
-__device__ __forceinline__ void apply_role(const Ctx& c, int role) {
-    const double2* __restrict__ yz = c.yz;
-    const double2* __restrict__ yp = c.yp;
-    const double2* __restrict__ yn = c.yn;
+__device__ __forceinline__ void apply_all(const Ctx& c) {
+    const double* __restrict__ yz = c.yz;
+    const double* __restrict__ yp = c.yp;
+    const double* __restrict__ yn = c.yn;
     const double2* __restrict__ fz = c.fz;
 #ifdef SFB_GTAB
     const double2* __restrict__ ktab = c.ktab;     // table entries: uniform-address 128-bit loads through L1
@@ -122,13 +126,12 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(scal + kNSc * kTN);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int group = warp / kR, role = warp % kR;
-    const int sb = lane >> 4;                       // 0: lane set A (m>=0), 1: lane set B (m<=0)
-    const int nl = group * 16 + (lane & 15);        // node within tile
+    const int sb = lane >> 4;                          // 0: sign set A (m>=0), 1: set B (m<=0)
+    const int comp = lane & 1;                         // 0: real part, 1: imaginary part
+    const int nl = warp * 8 + ((lane & 15) >> 1);      // node within tile
     const long long node0 = (long long)blockIdx.x * kTN;
     const int nvalid = (int)min((long long)kTN, P.N - node0);
 
-    // ---- stage the tile: one bulk copy per coefficient row into buffer 0
     const uint32_t mb = smem_u32(mbar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
@@ -140,9 +143,8 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
         if (lane == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes * (uint32_t)kNCoef) : "memory");
         for (int j = lane; j < kNCoef; j += 32) {
-            // (l,m) of global row j:  j = l(l+1)/2 + m, even l
             int l = 0;
-            while ((l + 2) * (l + 3) / 2 - (l + 2) <= j) l += 2;   // first row of degree l+2 is hrow(l+2)-(l+2)
+            while ((l + 2) * (l + 3) / 2 - (l + 2) <= j) l += 2;
             const int m = j - hrow(l);
             const int prow = 2 * pslot(l, m < 0 ? -m : m) + (m < 0 ? 1 : 0);
             const uint32_t dst = smem_u32(bufs + (size_t)prow * kTN);
@@ -151,9 +153,8 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
     }
-    // ---- meanwhile: per-node forcing
     prep_tile(P, node0, nvalid, tid, forc, scal);
-    {   // wait for the tile
+    {
         uint32_t done = 0;
         while (!done) {
             asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
@@ -170,26 +171,28 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
     c.ktab = nullptr;
 #endif
     c.valid = nl < nvalid;
+    c.sigma = comp ? 1.0 : -1.0;
     c.fz = forc + (size_t)sb * kNF * kTN + nl;
     c.lam = scal[SC_LAM * kTN + nl];
     c.rm = scal[SC_RM * kTN + nl];
     c.c0 = 0.0;
-    c.ld_out = P.ld_out;
-    c.sld = sb ? -P.ld_out : P.ld_out;
-    c.gout = P.nlm_out + node0 + nl;
-    c.gin = P.nlm_in + node0 + nl;
-    c.ld_in = P.ld_in;
-    c.sld_in = sb ? -P.ld_in : P.ld_in;
-    double2* acc = bufs + (size_t)(nbuf - 1) * kNRow * kTN + nl;
-    c.az = acc; c.ap = acc + sb * kTN;
+    c.ld_out = P.ld_out; c.sld = sb ? -P.ld_out : P.ld_out;
+    c.ld_in = P.ld_in;   c.sld_in = sb ? -P.ld_in : P.ld_in;
+    c.gout = reinterpret_cast<double*>(P.nlm_out + node0 + nl) + comp;
+    c.gin = reinterpret_cast<const double*>(P.nlm_in + node0 + nl) + comp;
+    double* dbuf = reinterpret_cast<double*>(bufs) + 2 * nl + comp;           // this lane's component column
+    constexpr size_t kBufD = (size_t)2 * kNRow * kTN;                          // doubles per buffer
+    constexpr int kPlane = 2 * kTN;                                            // doubles per physical row
+    double* acc = dbuf + (size_t)(nbuf - 1) * kBufD;
+    c.az = acc; c.ap = acc + sb * kPlane;
 
     for (int s = 0; s < P.nstage; ++s) {
-        // n0 is re-read from global (L2) in the later RK stages: inputs 0,1,0,1 ; outputs 1,0,1 ; accumulator 2
+        // RK4 (3 buffers, n0 re-read from global): inputs 0,1,0,1 ; outputs 1,0,1 ; accumulator 2
         const int ib = s & 1, ob = (s + 1) & 1;
-        const double2* yin = bufs + (size_t)ib * kNRow * kTN + nl;
-        double2* yout = bufs + (size_t)ob * kNRow * kTN + nl;
-        c.yz = yin; c.yp = yin + sb * kTN; c.yn = yin + (1 - sb) * kTN;
-        c.oz = yout; c.op = yout + sb * kTN;
+        const double* yin = dbuf + (size_t)ib * kBufD;
+        double* yout = dbuf + (size_t)ob * kBufD;
+        c.yz = yin; c.yp = yin + sb * kPlane; c.yn = yin + (1 - sb) * kPlane;
+        c.oz = yout; c.op = yout + sb * kPlane;
         c.first = (s == 0);
         c.last = (s == P.nstage - 1);
         c.ld_n0 = !c.first && c.valid && (SFB_HORNER || !c.last);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
         __syncthreads();
         c.c0 = scal[SC_C0 * kTN + nl];
 #endif
-        apply_role(c, role);
+        apply_all(c);
         if (!c.last) __syncthreads();
     }
 }
@@ -252,7 +255,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     const int nbuf = P.nstage == 1 ? 1 : nbuf_rk;
     const size_t smem = nbuf * per_buf + fixed;
     if (smem > lim) return cudaErrorInvalidConfiguration;
-    {   // regularisation constants live in this unit's __constant__ bank; refresh when they change
+    {
         static SfbRegConst last[64];
         static bool have[64] = {false};
         if (!have[dev] || memcmp(&last[dev], &reg, sizeof(SfbRegConst)) != 0) {

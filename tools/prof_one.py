@@ -6,7 +6,10 @@ import specfab_b200 as sf
 
 L, N, terms, scheme = int(sys.argv[1]), int(sys.argv[2]), tuple(sys.argv[3].split("+")), sys.argv[4]
 steps = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+variant = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 lm, n = sf.init(L)
+from specfab_b200 import _lib
+_lib.load().sfb_set_variant(variant)
 g = torch.Generator(device="cuda").manual_seed(1)
 nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
 nlm[0] = 0.2820947917738781

@@ -24,8 +24,12 @@ def run(L, N, terms, scheme, variants, steps=10):
             continue
         _lib.load().sfb_set_variant(v)
         out = torch.empty_like(nlm)
-        for _ in range(3):
-            sf.step_arr_dev(nlm, ug, tau, out=out, **kw)
+        try:
+            for _ in range(3):
+                sf.step_arr_dev(nlm, ug, tau, out=out, **kw)
+        except Exception as ex:
+            print(json.dumps(dict(L=L, variant=v, error=str(ex)[:120])), flush=True)
+            continue
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -46,8 +50,19 @@ def run(L, N, terms, scheme, variants, steps=10):
 
 
 if __name__ == "__main__":
-    V = list(range(0, 12))
-    run(8, 1_000_000, ("lrot", "reg"), "rk4", V)
-    run(8, 1_000_000, ("lrot", "reg"), "euler", V)
-    run(8, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
-    run(8, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
+    V = list(range(0, 20))
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "8"):
+        run(8, 1_000_000, ("lrot", "reg"), "rk4", V)
+        run(8, 1_000_000, ("lrot", "reg"), "euler", V)
+        run(8, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
+        run(8, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
+    if which in ("all", "12"):
+        run(12, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
+        run(12, 500_000, ("lrot", "reg"), "rk4", V)
+    if which in ("all", "20"):
+        run(20, 300_000, ("lrot", "ddrx", "cdrx", "reg"), "euler", V)
+        run(20, 300_000, ("lrot", "reg"), "euler", V)
+    if which in ("all", "4"):
+        run(4, 2_000_000, ("lrot", "reg"), "rk4", V)
+        run(4, 2_000_000, ("lrot", "ddrx", "reg"), "euler", V)
