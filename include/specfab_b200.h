@@ -110,6 +110,24 @@ int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const doubl
 int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
                                double* Eij, double* ei, double* lami, int32_t* status, void* stream);
 
+/* Batched operator export (the form the Eulerian FE couplers consume: src/specfabpy/fenics/CPO.py:200-202,
+ * src/specfabpy/firedrake/ice.py:202-204).  M is (N, nlm_len, nlm_len) in Fortran order, complex(8) for
+ * M_LROT / M_DDRX(_src), real(8) for M_REG.  eps, omg, tau: (N,3,3).
+ *   M_LROT(nlm, eps, omg, iota, zeta)      src/specfabpy.f90:172-180, src/dynamics.f90:52-97
+ *   M_DDRX_src(nlm, tau)                   src/specfabpy.f90:192-199, src/dynamics.f90:277-298
+ *   M_DDRX(nlm, tau) = M_DDRX_src - <D> I  src/specfabpy.f90:182-190, src/dynamics.f90:251-275
+ *   M_REG(nlm, eps)                        src/specfabpy.f90:237-245, src/dynamics.f90:494-518
+ *   M_CDRX(nlm) = diag(-l(l+1))            src/specfabpy.f90:228-235, src/dynamics.f90:474-492 (constant: host only) */
+int sfb_M_LROT_arr(const double* eps, const double* omg, int64_t N, double iota, double zeta, double* M);
+int sfb_M_LROT_arr_dev(const double* eps, const double* omg, int64_t N, int64_t ld, double iota, double zeta, double* M, void* stream);
+int sfb_M_DDRX_src_arr(const double* tau, int64_t N, double* M);
+int sfb_M_DDRX_src_arr_dev(const double* tau, int64_t N, int64_t ld, double* M, void* stream);
+int sfb_M_DDRX_arr(const double* nlm, int64_t ld_nlm, const double* tau, int64_t N, double* M);
+int sfb_M_DDRX_arr_dev(const double* nlm, int64_t ld_nlm, const double* tau, int64_t N, int64_t ld, double* M, void* stream);
+int sfb_M_REG_arr(const double* eps, int64_t N, double* M);
+int sfb_M_REG_arr_dev(const double* eps, int64_t N, int64_t ld, double* M, void* stream);
+int sfb_M_CDRX(double* M /* [nlm_len*nlm_len] */);
+
 /* tuning knob: select an alternative compiled kernel variant (0 = default); unknown ids fall back to 0 */
 int sfb_set_variant(int variant);
 

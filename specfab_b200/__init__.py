@@ -18,7 +18,8 @@ import numpy as np
 from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
-__all__ = ["init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
+__all__ = ["M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
+           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "Eij_eigenframe_arr", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
@@ -124,6 +125,91 @@ def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.
         raise ValueError("out must be a Fortran-ordered complex128 array of shape (N, nlm_len)")
     _lib.check(lib.sfb_step_arr(nlm_f.ctypes.data, out.ctypes.data, N, N, ug.ctypes.data,
                                 ta.ctypes.data if ta is not None else None, C.byref(o)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# operators (matrix form), reference: src/specfabpy.f90:172-245
+# ------------------------------------------------------------------------------------------
+
+def M_LROT_arr(eps, omg, iota, zeta):
+    """M_LROT of every node: eps, omg (N,3,3) -> (N,nlm_len,nlm_len) complex128 (Fortran order)"""
+    n = _need_init()
+    e, w = _farr(eps, np.float64, (3, 3)), _farr(omg, np.float64, (3, 3))
+    N = e.shape[0]
+    M = np.empty((N, n, n), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_M_LROT_arr(e.ctypes.data, w.ctypes.data, N, float(iota), float(zeta), M.ctypes.data))
+    return M
+
+
+def M_DDRX_src_arr(tau):
+    n = _need_init()
+    t = _farr(tau, np.float64, (3, 3))
+    N = t.shape[0]
+    M = np.empty((N, n, n), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_M_DDRX_src_arr(t.ctypes.data, N, M.ctypes.data))
+    return M
+
+
+def M_DDRX_arr(nlm, tau):
+    n = _need_init()
+    x = np.asfortranarray(np.asarray(nlm, dtype=np.complex128))
+    t = _farr(tau, np.float64, (3, 3))
+    N = t.shape[0]
+    if x.shape != (N, n):
+        raise ValueError("nlm must have shape (N, nlm_len)")
+    M = np.empty((N, n, n), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_M_DDRX_arr(x.ctypes.data, N, t.ctypes.data, N, M.ctypes.data))
+    return M
+
+
+def M_REG_arr(eps):
+    n = _need_init()
+    e = _farr(eps, np.float64, (3, 3))
+    N = e.shape[0]
+    M = np.empty((N, n, n), dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_M_REG_arr(e.ctypes.data, N, M.ctypes.data))
+    return M
+
+
+def M_LROT(nlm, eps, omg, iota, zeta):
+    """reference: src/specfabpy.f90:172-180 (nlm only fixes the size)"""
+    return np.ascontiguousarray(M_LROT_arr(np.asarray(eps)[None], np.asarray(omg)[None], iota, zeta)[0])
+
+
+def M_DDRX(nlm, tau):
+    """reference: src/specfabpy.f90:182-190 (multiply by Gamma0 yourself, like the reference)"""
+    return np.ascontiguousarray(M_DDRX_arr(np.asarray(nlm)[None, :], np.asarray(tau)[None])[0])
+
+
+def M_DDRX_src(nlm, tau):
+    """reference: src/specfabpy.f90:192-199"""
+    return np.ascontiguousarray(M_DDRX_src_arr(np.asarray(tau)[None])[0])
+
+
+def M_CDRX(nlm):
+    """reference: src/specfabpy.f90:228-235 (real diagonal; returned complex like the f2py wrapper)"""
+    n = _need_init()
+    M = np.zeros((n, n), dtype=np.float64)
+    _lib.check(_lib.load().sfb_M_CDRX(M.ctypes.data))
+    return M.astype(np.complex128)
+
+
+def M_REG(nlm, eps):
+    """reference: src/specfabpy.f90:237-245"""
+    return np.ascontiguousarray(M_REG_arr(np.asarray(eps)[None])[0])
+
+
+def nlm_LROT(nlm0, dt, Nt, D, W, iota):
+    """Euler integrator of lattice rotation for one parcel with time-dependent D(t), W(t) -> nlm (Nt, nlm_len)
+    reference: src/specfabpy.f90:260-268, src/dynamics.f90:99-110 (zeta = 0, no regularisation)"""
+    n = _need_init()
+    out = np.zeros((Nt, n), dtype=np.complex128)
+    out[0] = nlm0
+    cur = np.asarray(nlm0, dtype=np.complex128)[None, :]
+    for j in range(Nt - 1):
+        cur = step_arr(cur, (np.asarray(D[j]) + np.asarray(W[j]))[None], dt=dt, iota=iota, zeta=0.0, terms=("lrot",))
+        out[j + 1] = cur[0]
     return out
 
 

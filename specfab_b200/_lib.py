@@ -52,6 +52,15 @@ SIGNATURES = {
     "sfb_Eij_tranisotropic_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P]),
     "sfb_Eij_eigenframe_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P]),
     "sfb_Eij_eigenframe_arr_dev": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P]),
+    "sfb_M_LROT_arr": (C.c_int, [_P, _P, _I64, C.c_double, C.c_double, _P]),
+    "sfb_M_LROT_arr_dev": (C.c_int, [_P, _P, _I64, _I64, C.c_double, C.c_double, _P, _P]),
+    "sfb_M_DDRX_src_arr": (C.c_int, [_P, _I64, _P]),
+    "sfb_M_DDRX_src_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "sfb_M_DDRX_arr": (C.c_int, [_P, _I64, _P, _I64, _P]),
+    "sfb_M_DDRX_arr_dev": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, _P]),
+    "sfb_M_REG_arr": (C.c_int, [_P, _I64, _P]),
+    "sfb_M_REG_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "sfb_M_CDRX": (C.c_int, [_P]),
     "sfb_set_variant": (C.c_int, [C.c_int]),
     "sfb_dev_malloc": (C.c_int, [C.POINTER(_P), _I64]),
     "sfb_dev_free": (C.c_int, [_P]),

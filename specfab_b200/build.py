@@ -151,7 +151,7 @@ def build(Ls=None, jobs=None, verbose=False):
     Ls = Ls or ALL_L
     jobs = jobs or max(1, (os.cpu_count() or 2))
     units, metas = generate(Ls)
-    units = units + [os.path.join(CSRC, "sfb_api.cu"), os.path.join(CSRC, "sfb_fields.cu")]
+    units = units + [os.path.join(CSRC, "sfb_api.cu"), os.path.join(CSRC, "sfb_fields.cu"), os.path.join(CSRC, "sfb_operators.cu")]
     objs = []
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
         for obj, dt, log in ex.map(lambda s: compile_one(s, verbose), units):

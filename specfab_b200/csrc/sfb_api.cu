@@ -10,6 +10,10 @@
 #include "sfb_fields.cuh"
 #include "specfab_b200.h"
 
+cudaError_t sfb_launch_mexport(int mode, int L, const double* a33, const double* b33, const double2* nlm, long long ldn,
+                               long long N, long long ld, double iota, double zeta, double2* M, cudaStream_t st);
+cudaError_t sfb_launch_mreg(int L, const SfbRegConst& reg, const double* eps, long long N, long long ld, double* M, cudaStream_t st);
+void sfb_ops_release();
 cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
@@ -130,6 +134,7 @@ int sfb_get_lm(int32_t* lm) {
 void sfb_finalize(void) {
     std::lock_guard<std::mutex> lk(g.mu);
     g_stage.release();
+    sfb_ops_release();
     g.L = 0; g.n = 0;
 }
 
@@ -455,6 +460,88 @@ int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const doubl
         CK(cudaMemcpy(lami, o2.p, (size_t)N * 3 * 8, cudaMemcpyDeviceToHost));
     }
     if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operator export: dense (N, n, n) operators, Fortran order (node contiguous)
+// ---------------------------------------------------------------------------------------------
+static int mexport_dev(int mode, const double* a33, const double* b33, const double* nlm, int64_t ldn, int64_t N, int64_t ld,
+                       double iota, double zeta, double* M, void* stream) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    if (N == 0) return SFB_OK;
+    if (!a33 || !M || (mode == 0 && !b33) || (mode == 2 && (!nlm || ldn < N))) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_mexport(mode, g.L, a33, b33, reinterpret_cast<const double2*>(nlm), ldn, N, ld, iota, zeta,
+                          reinterpret_cast<double2*>(M), (cudaStream_t)stream));
+    return SFB_OK;
+}
+static int mexport_host(int mode, const double* a33, const double* b33, const double* nlm, int64_t ldn, int64_t N,
+                        double iota, double zeta, double* M) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (N == 0) return SFB_OK;
+    if (!a33 || !M || (mode == 0 && !b33) || (mode == 2 && !nlm)) return fail(SFB_EINVAL, "null array");
+    DevTmp da, db, dn, dm;
+    int rc;
+    CK(da.alloc((size_t)N * 72));
+    CK(cudaMemcpy(da.p, a33, (size_t)N * 72, cudaMemcpyHostToDevice));
+    if (mode == 0) { CK(db.alloc((size_t)N * 72)); CK(cudaMemcpy(db.p, b33, (size_t)N * 72, cudaMemcpyHostToDevice)); }
+    if (mode == 2 && (rc = stage_rows(dn, nlm, N, ldn, 15))) return rc;
+    const size_t mbytes = (size_t)N * g.n * g.n * 16;
+    CK(dm.alloc(mbytes));
+    rc = mexport_dev(mode, da.as<double>(), db.as<double>(), dn.as<double>(), N, N, N, iota, zeta, dm.as<double>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(M, dm.p, mbytes, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_M_LROT_arr(const double* eps, const double* omg, int64_t N, double iota, double zeta, double* M) {
+    return mexport_host(0, eps, omg, nullptr, 0, N, iota, zeta, M);
+}
+int sfb_M_LROT_arr_dev(const double* eps, const double* omg, int64_t N, int64_t ld, double iota, double zeta, double* M, void* stream) {
+    return mexport_dev(0, eps, omg, nullptr, 0, N, ld, iota, zeta, M, stream);
+}
+int sfb_M_DDRX_src_arr(const double* tau, int64_t N, double* M) { return mexport_host(1, tau, nullptr, nullptr, 0, N, 0, 0, M); }
+int sfb_M_DDRX_src_arr_dev(const double* tau, int64_t N, int64_t ld, double* M, void* stream) {
+    return mexport_dev(1, tau, nullptr, nullptr, 0, N, ld, 0, 0, M, stream);
+}
+int sfb_M_DDRX_arr(const double* nlm, int64_t ldn, const double* tau, int64_t N, double* M) {
+    return mexport_host(2, tau, nullptr, nlm, ldn, N, 0, 0, M);
+}
+int sfb_M_DDRX_arr_dev(const double* nlm, int64_t ldn, const double* tau, int64_t N, int64_t ld, double* M, void* stream) {
+    return mexport_dev(2, tau, nullptr, nlm, ldn, N, ld, 0, 0, M, stream);
+}
+int sfb_M_REG_arr_dev(const double* eps, int64_t N, int64_t ld, double* M, void* stream) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    if (N == 0) return SFB_OK;
+    if (!eps || !M) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_mreg(g.L, g.reg, eps, N, ld, M, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_M_REG_arr(const double* eps, int64_t N, double* M) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (N == 0) return SFB_OK;
+    if (!eps || !M) return fail(SFB_EINVAL, "null array");
+    DevTmp de, dm;
+    CK(de.alloc((size_t)N * 72));
+    CK(cudaMemcpy(de.p, eps, (size_t)N * 72, cudaMemcpyHostToDevice));
+    const size_t mbytes = (size_t)N * g.n * g.n * 8;
+    CK(dm.alloc(mbytes));
+    int rc = sfb_M_REG_arr_dev(de.as<double>(), N, N, dm.as<double>(), nullptr);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(M, dm.p, mbytes, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_M_CDRX(double* M) {      // constant operator diag(-l(l+1)), src/dynamics.f90:474-492 (no per-node input)
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (!M) return fail(SFB_EINVAL, "null array");
+    memset(M, 0, sizeof(double) * g.n * g.n);
+    int j = 0;
+    for (int l = 0; l <= g.L; l += 2)
+        for (int m = -l; m <= l; ++m, ++j) M[(size_t)j * g.n + j] = -(double)(l * (l + 1));
     return SFB_OK;
 }
 

@@ -166,7 +166,9 @@ __device__ __forceinline__ void mat_to_vec(const double t[3][3], double v[6]) {
 }
 __device__ __forceinline__ void vec_to_mat(const double v[6], double t[3][3]) {
     t[0][0] = v[0]; t[1][1] = v[1]; t[2][2] = v[2];
-    t[0][1] = t[1][0] = v[5] / SFB_SQRT2; t[0][2] = t[2][0] = v[4] / SFB_SQRT2; t[1][2] = t[2][1] = v[3] / SFB_SQRT2;
+    // v/sqrt(2) as a multiplication by the correctly rounded reciprocal (<= 1 ulp from the reference's division)
+    const double r2 = 0.7071067811865476;
+    t[0][1] = t[1][0] = v[5] * r2; t[0][2] = t[2][0] = v[4] * r2; t[1][2] = t[2][1] = v[3] * r2;
 }
 __device__ __forceinline__ double dinner22(const double A[3][3], const double B[3][3]) {   // A_ij B_ji
     double s = 0.0;
@@ -201,20 +203,21 @@ __device__ __forceinline__ int potf2_lower(double a[6][6]) {
     }
     return 0;
 }
-__device__ __forceinline__ void potrs_lower(const double a[6][6], double x[6]) {
+// triangular solves with the reciprocal pivots computed once per node (6 divisions instead of 12 per solve)
+__device__ __forceinline__ void potrs_lower(const double a[6][6], const double invd[6], double x[6]) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         double s = x[i];
 #pragma unroll
         for (int k = 0; k < 6; ++k) if (k < i) s -= a[i][k] * x[k];
-        x[i] = s / a[i][i];
+        x[i] = s * invd[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = x[i];
 #pragma unroll
         for (int k = 0; k < 6; ++k) if (k > i) s -= a[k][i] * x[k];
-        x[i] = s / a[i][i];
+        x[i] = s * invd[i];
     }
 }
 
@@ -252,7 +255,7 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
 #pragma unroll
         for (int j = 0; j < 6; ++j) F[i][j] = P[i][j];
     const int info = potf2_lower(F);
-    double R[6][6];     // regularised normal matrix (only if the factorisation failed)
+    double R[6][6] = {};  // regularised normal matrix (only if the factorisation failed)
     if (info != 0) {    // src/homogenizations.f90:177-185: P_reg = P^T P + 1e-6 I using the partially factorised P
         status |= SFB_ST_TAYLOR_FALLBACK;
 #pragma unroll
@@ -266,6 +269,10 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
             }
         if (potf2_lower(R) != 0) status |= SFB_ST_TAYLOR_FAILED;
     }
+    double invd[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) invd[i] = 1.0 / (info == 0 ? F[i][i] : R[i][i]);
+    const double inv_t_iso = 1.0 / K.t_iso;
     bool finite = true;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
@@ -314,7 +321,7 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
         if (info == 0) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) x[i] = tv[i];
-            potrs_lower(F, x);
+            potrs_lower(F, invd, x);
         } else {
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
@@ -323,14 +330,14 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
                 for (int k = 0; k < 6; ++k) s += F[k][i] * tv[k];
                 x[i] = s;
             }
-            potrs_lower(R, x);
+            potrs_lower(R, invd, x);
         }
         double et[3][3], eti[3][3];
         vec_to_mat(x, et);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) eti[i][j] = tau[i][j] / K.t_iso;
+            for (int j = 0; j < 3; ++j) eti[i][j] = tau[i][j] * inv_t_iso;
         const double Et = dinner22(et, vw) / dinner22(eti, vw);
         E[q] = (1 - K.alpha) * Es + K.alpha * Et;
         finite = finite && isfinite(E[q]);

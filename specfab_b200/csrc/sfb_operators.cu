@@ -1,0 +1,253 @@
+// Batched operator export: M_LROT, M_DDRX_src, M_DDRX, M_REG as dense (N, n, n) arrays, the form the
+// reference's Eulerian callers consume (src/specfabpy/fenics/CPO.py:200-202, firedrake/ice.py:202-204;
+// SURVEY.md section 8f-1).  One thread per node, node-contiguous (coalesced) stores of every non-zero
+// M(i,j); the per-L coefficient lists are merged on the host at init from the embedded Gaunt data with
+// the algebra of codegen/operators.py:
+//     M_LROT(i,j) = qe[D]*A(i,j) + (i*qo[D])*B(i,j),  D = m_i - m_j        src/dynamics.f90:78-96
+//     M_DDRX_src(i,j) = sum_lk g[(lk,D)] * GC(i,j,(lk,D))                   src/dynamics.f90:295-297
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "sfb_common.cuh"
+#include "sfb_moments.cuh"
+#include "gen/tables.inc"
+
+struct SfbNz {           // one structurally non-zero M(i,j): value = sum_t c[t] * f[fidx[t]]
+    int i, j, nt;
+    int fidx[3];
+    double c[3];
+};
+
+namespace {
+
+constexpr int kNMax = 231, kNCat = 15;
+std::vector<double> g_dense[4];    // GC, GCm, GC_m1, GC_p1 dense [231][231][15] (host, built once)
+
+void build_dense() {
+    if (!g_dense[0].empty()) return;
+    const int N[4] = {kGauntN_0, kGauntN_1, kGauntN_2, kGauntN_3};
+    const unsigned short* I[4] = {kGauntI_0, kGauntI_1, kGauntI_2, kGauntI_3};
+    const unsigned short* J[4] = {kGauntJ_0, kGauntJ_1, kGauntJ_2, kGauntJ_3};
+    const unsigned char* K[4] = {kGauntK_0, kGauntK_1, kGauntK_2, kGauntK_3};
+    const float* V[4] = {kGauntV_0, kGauntV_1, kGauntV_2, kGauntV_3};
+    for (int t = 0; t < 4; ++t) {
+        g_dense[t].assign((size_t)kNMax * kNMax * kNCat, 0.0);
+        for (int e = 0; e < N[t]; ++e) g_dense[t][((size_t)I[t][e] * kNMax + J[t][e]) * kNCat + K[t][e]] = (double)V[t][e];
+    }
+}
+inline double T(int t, int i, int j, int k) { return g_dense[t][((size_t)i * kNMax + j) * kNCat + k]; }
+
+struct DevLists {
+    int L = 0;
+    SfbNz *lrot = nullptr, *ddrx = nullptr;
+    int n_lrot = 0, n_ddrx = 0;
+} g_lists[64];
+
+// real(4) constants of src/dynamics.f90:79-86 promoted to double
+const double SQRT3_F = 0x1.bb67aep+0, S56 = 0x1.d363d2p-1, S23 = 0x1.a20bd8p-1, S32 = 0x1.3988e2p+0;
+const double C6 = 6.0 / 0x1.3988e2p+1;
+
+void merge_lists(int L, std::vector<SfbNz>& lrot, std::vector<SfbNz>& ddrx) {
+    build_dense();
+    const int n = (L + 1) * (L + 2) / 2;
+    std::vector<int> mm(n);
+    {
+        int j = 0;
+        for (int l = 0; l <= L; l += 2)
+            for (int m = -l; m <= l; ++m) mm[j++] = m;
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            const int D = mm[i] - mm[j];
+            if (D >= -2 && D <= 2) {
+                double A = 0, B = 0;
+                // same expressions as codegen/operators.py (GC=0, GCm=1, GC_m1=2, GC_p1=3)
+                if (D == -2) A = -(3 * T(0, i, j, 1) - T(1, i, j, 1) + T(2, i, j, 2));
+                if (D == -1) A = -(3 * T(0, i, j, 2) + S56 * T(2, i, j, 0) + S23 * T(2, i, j, 3) + 2 * T(3, i, j, 1));
+                if (D == 0) A = -(3 * T(0, i, j, 3) + S32 * T(2, i, j, 4) + S32 * T(3, i, j, 2));
+                if (D == 1) A = -(3 * T(0, i, j, 4) + 2 * T(2, i, j, 5) + S56 * T(3, i, j, 0) + S23 * T(3, i, j, 3));
+                if (D == 2) A = -(3 * T(0, i, j, 5) + T(1, i, j, 5) + T(3, i, j, 4));
+                if (D == 0) B = SQRT3_F * T(1, i, j, 0);
+                if (D == -1) B = C6 * T(2, i, j, 0);
+                if (D == 1) B = -C6 * T(3, i, j, 0);
+                if (A != 0 || B != 0) {
+                    SfbNz z{}; z.i = i; z.j = j; z.nt = 0;
+                    if (A != 0) { z.fidx[z.nt] = D + 2; z.c[z.nt++] = A; }
+                    if (B != 0) { z.fidx[z.nt] = 5 + D + 1; z.c[z.nt++] = B; }
+                    lrot.push_back(z);
+                }
+            }
+            if (D >= -4 && D <= 4) {
+                SfbNz z{}; z.i = i; z.j = j; z.nt = 0;
+                const int lks[3] = {0, 2, 4}, base[3] = {0, 3, 10};     // k(lk,mk) = base + mk
+                for (int q = 0; q < 3; ++q) {
+                    if (lks[q] < (D < 0 ? -D : D)) continue;
+                    const int k = base[q] + D;
+                    const double c = T(0, i, j, k);
+                    if (c != 0) { z.fidx[z.nt] = 8 + k; z.c[z.nt++] = c; }
+                }
+                if (z.nt) ddrx.push_back(z);
+            }
+        }
+}
+
+#define SFB_L 20          // sfb_step_common.cuh needs compile-time names; only the forcing helpers are used here
+#define SFB_DDRX 1
+constexpr int kTN = 128;   // nodes per block
+constexpr int kNF = 23;
+constexpr int kThreads = 128;
+__constant__ SfbRegConst c_reg;
+enum { SC_C0 = 0, SC_LAM = 1, SC_RM = 2, SC_G0 = 3, SC_TAUV = 4, SC_TSQV = 10, SC_NORM = 16 };
+#include "sfb_step_common.cuh"
+
+// mode 0: M_LROT(eps, omg, iota, zeta)   mode 1: M_DDRX_src(tau)   mode 2: M_DDRX(nlm, tau)
+__global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNz* __restrict__ nz, int nnz, int n,
+                                                           const double* __restrict__ a33, const double* __restrict__ b33,
+                                                           const double2* __restrict__ nlm, long long ldn, long long N, long long ld,
+                                                           double iota, double zeta, double2* __restrict__ M, long long ldm) {
+    __shared__ double2 f[kNF][kTN];
+    const int t = threadIdx.x;
+    const long long p = (long long)blockIdx.x * kTN + t;
+    const bool ok = p < N;
+    double davg = 0.0;
+    if (ok) {
+        if (mode == 0) {
+            // reference reads eps / omg entries directly: quad_rr(iota*eps + zetanorm*eps^2), quad_tp(omg)
+            double e[3][3], w[3][3], sq[3][3], E[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { e[i][j] = a33[(long long)(i + 3 * j) * ld + p]; w[i][j] = b33[(long long)(i + 3 * j) * ld + p]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) sq[i][j] = e[i][0] * e[0][j] + e[i][1] * e[1][j] + e[i][2] * e[2][j];
+            const double zetanorm = zeta / sqrt(sq[0][0] + sq[1][1] + sq[2][2]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) E[i][j] = iota * e[i][j] + zetanorm * sq[i][j];
+            double2 qe[5], qo[3];
+            quad_rr(E, qe);
+            quad_tp(w, qo);
+#pragma unroll
+            for (int d = 0; d < 5; ++d) f[d][t] = qe[d];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) f[5 + d][t] = make_double2(-qo[d].y, qo[d].x);     // i*qo
+        } else {
+            double T3[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) T3[i][j] = a33[(long long)(i + 3 * j) * ld + p];
+            double2 qt[5], g[15];
+            quad_rr(T3, qt);
+            ddrx_weights_raw(qt, g);
+            double dd = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dd += T3[i][j] * T3[j][i];
+            const double kk = 0x1.14d2dcd9ceb17p-3;
+#pragma unroll
+            for (int k = 0; k < 15; ++k) f[8 + k][t] = make_double2(((kk * g[k].x) * 5) / dd, ((kk * g[k].y) * 5) / dd);
+            if (mode == 2) {      // <D>  (src/dynamics.f90:402-422)
+                double sq[3][3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) sq[i][j] = T3[i][0] * T3[0][j] + T3[i][1] * T3[1][j] + T3[i][2] * T3[2][j];
+                const double tv[6] = {T3[0][0], T3[1][1], T3[2][2], SFB_SQRT2 * T3[1][2], SFB_SQRT2 * T3[0][2], SFB_SQRT2 * T3[0][1]};
+                const double sv[6] = {sq[0][0], sq[1][1], sq[2][2], SFB_SQRT2 * sq[1][2], SFB_SQRT2 * sq[0][2], SFB_SQRT2 * sq[0][1]};
+                double2 n2[3], n4[5];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ldn + p];
+#pragma unroll
+                for (int m = 0; m < 5; ++m) n4[m] = nlm[(long long)(10 + m) * ldn + p];
+                davg = sfb::ev_D2(nlm[p], n2, n4, tv, sv, sq[0][0] + sq[1][1] + sq[2][2]);
+            }
+        }
+    }
+    if (!ok) return;
+    for (int z = blockIdx.y; z < nnz; z += gridDim.y) {
+        const SfbNz e = nz[z];
+        double2 v = make_double2(0.0, 0.0);
+        for (int q = 0; q < e.nt; ++q) {
+            const double2 ff = f[e.fidx[q]][t];
+            v.x = fma(e.c[q], ff.x, v.x);
+            v.y = fma(e.c[q], ff.y, v.y);
+        }
+        if (mode == 2 && e.i == e.j) v.x -= davg;
+        M[((long long)e.i + (long long)n * e.j) * ldm + p] = v;
+    }
+}
+
+__global__ void mreg_kernel(const double* __restrict__ eps, long long N, long long ld, int n, int L, double nu,
+                            const double* __restrict__ regdiag_l, double* __restrict__ M, long long ldm) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    double fro = 0.0;
+    for (int q = 0; q < 9; ++q) { const double v = eps[(long long)q * ld + p]; fro += v * v; }
+    const double ratemag = nu * sqrt(fro);                      // src/dynamics.f90:516
+    int j = 0;
+    for (int l = 0; l <= L; l += 2)
+        for (int m = -l; m <= l; ++m, ++j) M[((long long)j + (long long)n * j) * ldm + p] = -ratemag * regdiag_l[l / 2];
+}
+
+}  // namespace
+
+cudaError_t sfb_ops_prepare(int L) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    DevLists& d = g_lists[dev];
+    if (d.L == L) return cudaSuccess;
+    std::vector<SfbNz> a, b;
+    merge_lists(L, a, b);
+    cudaFree(d.lrot); cudaFree(d.ddrx);
+    d = DevLists();
+    cudaError_t e;
+    if ((e = cudaMalloc(&d.lrot, a.size() * sizeof(SfbNz))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d.ddrx, b.size() * sizeof(SfbNz))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.lrot, a.data(), a.size() * sizeof(SfbNz), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.ddrx, b.data(), b.size() * sizeof(SfbNz), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    d.n_lrot = (int)a.size(); d.n_ddrx = (int)b.size(); d.L = L;
+    return cudaSuccess;
+}
+
+void sfb_ops_release() {
+    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); d = DevLists(); }
+}
+
+// M must be zero-filled by the caller side of the launcher (done here with cudaMemsetAsync)
+cudaError_t sfb_launch_mexport(int mode, int L, const double* a33, const double* b33, const double2* nlm, long long ldn,
+                               long long N, long long ld, double iota, double zeta, double2* M, cudaStream_t st) {
+    cudaError_t e = sfb_ops_prepare(L);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const DevLists& d = g_lists[dev & 63];
+    const int n = (L + 1) * (L + 2) / 2;
+    if ((e = cudaMemsetAsync(M, 0, (size_t)N * n * n * sizeof(double2), st)) != cudaSuccess) return e;
+    if (N <= 0) return cudaSuccess;
+    const SfbNz* nz = mode == 0 ? d.lrot : d.ddrx;
+    const int nnz = mode == 0 ? d.n_lrot : d.n_ddrx;
+    dim3 grid((unsigned)((N + kTN - 1) / kTN), (unsigned)std::min(nnz, 64));
+    mexport_kernel<<<grid, kThreads, 0, st>>>(mode, nz, nnz, n, a33, b33, nlm, ldn, N, ld, iota, zeta, M, N);
+    return cudaGetLastError();
+}
+
+cudaError_t sfb_launch_mreg(int L, const SfbRegConst& reg, const double* eps, long long N, long long ld, double* M, cudaStream_t st) {
+    const int n = (L + 1) * (L + 2) / 2;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(M, 0, (size_t)N * n * n * sizeof(double), st)) != cudaSuccess) return e;
+    if (N <= 0) return cudaSuccess;
+    double* dreg = nullptr;
+    if ((e = cudaMallocAsync(&dreg, sizeof(reg.regdiag), st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(dreg, reg.regdiag, sizeof(reg.regdiag), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    mreg_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(eps, N, ld, n, L, reg.nu, dreg, M, N);
+    e = cudaGetLastError();
+    cudaFreeAsync(dreg, st);
+    return e;
+}
