@@ -40,6 +40,13 @@ def lib():
         _lib.orc_step_batch.restype = C.c_int
         _lib.orc_step_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(Opts), C.c_int]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_set_num_threads.argtypes = [C.c_int]
+        # use every host core we may run on (torchrun exports OMP_NUM_THREADS=1 for multi-rank launches)
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        _lib.orc_set_num_threads(ncpu)
     return _lib
 
 

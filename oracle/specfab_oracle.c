@@ -34,6 +34,14 @@ static const double REG_NU[9] = {1.9879322126397958, 3.0011508426238862, 5.74980
                                  10.6068117205577668, 13.3591023418822363, 15.3094482670021108, 16.4844589176829217,
                                  19.9467342880730136}; /* src/include/regcalib.f90:1-36 */
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

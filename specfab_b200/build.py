@@ -30,19 +30,14 @@ ALL_L = [4, 6, 8, 10, 12, 14, 16, 18, 20]
 # tuning table: (L, ddrx) -> (roles R, tile nodes TN, min CTAs/SM for __launch_bounds__)
 # variant 0 is the default; extra variants (EXTRA) are selectable with sfb_set_variant() for tuning runs
 EXTRA = {
-    # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]   R = 0 selects the four-lane kernel
-    (8, 1): [(1, 1, 16, 6, "imm", False), (2, 1, 32, 3, "imm", False), (10, 0, 64, 2, "imm", True), (11, 0, 32, 4, "imm", True),
-             (12, 0, 16, 6, "imm", True), (13, 0, 128, 1, "imm", True)],
-    (12, 0): [(1, 1, 16, 4, "imm", False), (2, 1, 32, 2, "imm", False), (10, 0, 16, 4, "imm+w", True), (11, 0, 32, 2, "imm+w", True),
-              (12, 0, 8, 6, "imm+w", True)],
-    (12, 1): [(1, 1, 16, 4, "imm", False), (2, 2, 16, 3, "imm", False), (10, 0, 16, 4, "imm", True), (11, 0, 32, 2, "imm", True),
-              (12, 0, 8, 6, "imm", True), (13, 0, 64, 1, "imm", True)],
-    (20, 0): [(1, 1, 16, 3, "imm", False), (2, 2, 16, 3, "imm", False), (10, 0, 16, 3, "imm", True), (11, 0, 8, 6, "imm", True),
-              (12, 0, 32, 1, "imm", True)],
-    (20, 1): [(1, 1, 16, 2, "imm", False), (2, 2, 16, 2, "imm", False), (10, 0, 16, 2, "imm", True), (11, 0, 8, 5, "imm", True),
-              (12, 0, 32, 1, "imm", True)],
-    (4, 0): [(1, 1, 32, 8, "imm", False), (10, 0, 16, 8, "imm+w", True)],
-    (4, 1): [(1, 1, 32, 8, "imm", False), (10, 0, 16, 8, "imm", True), (11, 0, 64, 2, "imm", True)],
+    # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]
+    #   R = 0: four-lane kernel, R = -1: persistent four-lane kernel, R = -2: table-driven loop kernel
+    (8, 0): [(30, -2, 16, 6, "imm+ch2", False), (31, -2, 32, 3, "imm+ch2", False)],
+    (8, 1): [(30, -2, 16, 6, "imm+ch2", False), (31, -2, 32, 3, "imm+ch2", False), (32, -2, 64, 2, "imm+ch2", False)],
+    (12, 0): [(30, -2, 16, 6, "imm+ch2", False), (31, -2, 32, 3, "imm+ch2", False)],
+    (12, 1): [(30, -2, 16, 4, "imm+ch2", False), (31, -2, 32, 2, "imm+ch2", False), (32, -2, 16, 4, "imm+ch4", False), (33, -2, 48, 1, "imm+ch2", False)],
+    (20, 0): [(30, -2, 16, 3, "imm+ch2", False), (31, -2, 16, 3, "imm+ch4", False), (32, -2, 32, 1, "imm+ch2", False)],
+    (20, 1): [(30, -2, 16, 2, "imm+ch2", False), (31, -2, 16, 2, "imm+ch4", False), (32, -2, 32, 1, "imm+ch2", False)],
 }
 # default variant (0).  ncu (profiles/r01_notes.md): small tiles with several independent CTAs per SM hide the
 # per-tile load / prep phases; the DDRX kernels prefer four lanes per node (more threads per resident node).
@@ -83,9 +78,21 @@ def generate(Ls):
                 parts = cmode.split("+")
                 cm = parts[0]
                 window = "w" in parts[1:]
-                mc = max([int(x[1:]) for x in parts[1:] if x.startswith("c")] + [1])
+                mc = max([int(x[1:]) for x in parts[1:] if x.startswith("c") and not x.startswith("ch")] + [1])
                 gd = max([int(x[1:]) for x in parts[1:] if x.startswith("g")] + [0])
-                if R == 0:
+                if R == -2:      # table-driven loop kernel (two lanes per node); MINB field = CTAs/SM, "chN" = rows per chunk
+                    ch = max([int(x[2:]) for x in parts[1:] if x.startswith("ch")] + [2])
+                    tabsrc, meta = emit_step.emit_loop_table(L, dd, ch)
+                    meta.update(TN=TN, dfma_role=[0], dfma_node=2 * sum(p.dfma for p in emit_step.plan(L, dd)[1]), loads_node=0, nrow=emit_step.nrow_phys(L))
+                    body = "// loop kernel: no generated body\n"
+                    tab = "#define SFB_LOOP 1\n#define SFB_CH %d\n" % ch + tabsrc
+                    skeleton = "sfb_step_kernel.cuh"
+                    R = 1
+                elif R == -1:      # persistent, lock-stepped, streaming refill (four lanes per node)
+                    body, tab, meta = emit_step.emit4(L, dd, TN, cm, True, window, mc, gd)
+                    skeleton = "sfb_step_kernel5.cuh"
+                    tab = "#define SFB_WINDOW %d\n" % int(window) + tab
+                elif R == 0:
                     body, tab, meta = emit_step.emit4(L, dd, TN, cm, sync, window, mc, gd)
                     skeleton = "sfb_step_kernel4.cuh"
                 else:

@@ -23,6 +23,7 @@ struct SfbStepParams {
     int nstage;              // 1 = Euler, 4 = classical RK4
     int use_lrot, use_reg;
     const double2* ktab;     // set by the launcher in gtab mode
+    int raw_ok;              // set by the launcher: forcing planes can be staged with 1-D TMA bulk copies
     int n0_global;           // set by the launcher: RK4 re-reads n0 from global (3 smem buffers)
 };
 

@@ -68,33 +68,43 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // (task = tid / kTN is warp uniform for kTN >= 32):
 //   task 0: M_LROT weights + M_REG / M_CDRX scalars      task 1: DDRX weights g      task 2: <D> ingredients
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_sym_skew(const SfbStepParams& P, long long node, double D[3][3], double W[3][3]) {
+// where a node's 3x3 forcing matrices are read from: global arrays (stride = leading dimension) or the
+// TMA-staged shared-memory copy of the tile (stride = kTN); element (i,k) at base[(i+3k)*stride]
+struct ForcSrc {
+    const double* ug; long long su;
+    const double* tau; long long st;      // tau == nullptr -> tau := D
+};
+__device__ __forceinline__ ForcSrc global_src(const SfbStepParams& P, long long node) {
+    ForcSrc s; s.ug = P.ugrad + node; s.su = P.ld_u; s.tau = P.tau ? P.tau + node : nullptr; s.st = P.ld_t; return s;
+}
+
+__device__ __forceinline__ void load_sym_skew(const ForcSrc& S, double D[3][3], double W[3][3]) {
     double u[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) u[i][j] = P.ugrad[(long long)(i + 3 * j) * P.ld_u + node];
+        for (int j = 0; j < 3; ++j) u[i][j] = S.ug[(long long)(i + 3 * j) * S.su];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) { D[i][j] = (u[i][j] + u[j][i]) / 2; W[i][j] = (u[i][j] - u[j][i]) / 2; }
 }
 
-__device__ __forceinline__ void load_tau(const SfbStepParams& P, long long node, double T[3][3]) {
-    if (P.tau) {
+__device__ __forceinline__ void load_tau(const ForcSrc& S, double T[3][3]) {
+    if (S.tau) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) T[i][j] = P.tau[(long long)(i + 3 * j) * P.ld_t + node];
+            for (int j = 0; j < 3; ++j) T[i][j] = S.tau[(long long)(i + 3 * j) * S.st];
     } else {   // tau := D (src/specfabpy/integrator.py:39)
         double W[3][3];
-        load_sym_skew(P, node, T, W);
+        load_sym_skew(S, T, W);
     }
 }
 
-__device__ void prep_lrot(const SfbStepParams& P, long long node, int t, double2* forc, double* scal) {
+__device__ void prep_lrot(const SfbStepParams& P, const ForcSrc& S, long long node, int t, double2* forc, double* scal) {
     double D[3][3], W[3][3];
-    load_sym_skew(P, node, D, W);
+    load_sym_skew(S, D, W);
     double2* fA = forc + t;                    // lane set A block: entry e at fA[e*kTN]
     double2* fB = forc + kNF * kTN + t;        // lane set B block
     // ---- M_LROT weights, src/dynamics.f90:71-76
@@ -137,13 +147,13 @@ __device__ void prep_lrot(const SfbStepParams& P, long long node, int t, double2
 }
 
 #if SFB_DDRX
-__device__ void prep_ddrx_g(const SfbStepParams& P, long long node, int t, double2* forc, double* scal) {
+__device__ void prep_ddrx_g(const SfbStepParams& P, const ForcSrc& S, long long node, int t, double2* forc, double* scal) {
     double2* fA = forc + t;
     double2* fB = forc + kNF * kTN + t;
     const double g0 = P.gamma0_arr ? P.gamma0_arr[node] : P.gamma0;
     scal[SC_G0 * kTN + t] = g0;
     double T[3][3];
-    load_tau(P, node, T);
+    load_tau(S, T);
     double2 qt[5], g[15];
     quad_rr(T, qt);
     ddrx_weights_raw(qt, g);
@@ -161,10 +171,10 @@ __device__ void prep_ddrx_g(const SfbStepParams& P, long long node, int t, doubl
     for (int k = 0; k < 15; ++k) { fA[(8 + k) * kTN] = g[k]; fB[(8 + k) * kTN] = g[cat_mirror(k)]; }
 }
 
-__device__ void prep_ddrx_d(const SfbStepParams& P, long long node, int t, double* scal) {
+__device__ void prep_ddrx_d(const ForcSrc& S, int t, double* scal) {
     // <D> ingredients, src/dynamics.f90:415-417
     double T[3][3];
-    load_tau(P, node, T);
+    load_tau(S, T);
     double sq[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -182,14 +192,15 @@ __device__ void prep_ddrx_d(const SfbStepParams& P, long long node, int t, doubl
 __device__ __forceinline__ void prep_tile(const SfbStepParams& P, long long node0, int nvalid, int tid, double2* forc, double* scal) {
     const int task = tid / kTN, t = tid - task * kTN;
     if (t >= nvalid) return;
-    if (task == 0) prep_lrot(P, node0 + t, t, forc, scal);
+    const ForcSrc S = global_src(P, node0 + t);
+    if (task == 0) prep_lrot(P, S, node0 + t, t, forc, scal);
 #if SFB_DDRX
     if (kThreads >= 3 * kTN) {
-        if (task == 1) prep_ddrx_g(P, node0 + t, t, forc, scal);
-        if (task == 2) prep_ddrx_d(P, node0 + t, t, scal);
+        if (task == 1) prep_ddrx_g(P, S, node0 + t, t, forc, scal);
+        if (task == 2) prep_ddrx_d(S, t, scal);
     } else if (task == 1) {
-        prep_ddrx_g(P, node0 + t, t, forc, scal);
-        prep_ddrx_d(P, node0 + t, t, scal);
+        prep_ddrx_g(P, S, node0 + t, t, forc, scal);
+        prep_ddrx_d(S, t, scal);
     }
 #endif
 }

@@ -98,8 +98,12 @@ __device__ __forceinline__ void row_out(const Ctx& c, double kr, double ki, doub
 #define SFB_ROW_PRE(l, mu, q, r) const double2 q = n0_load<l, mu>(c), r = acc_load<l, mu>(c)
 #define SFB_ROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out<l, mu>(c, ar, ai, zr, zi, q, r)
 // keeps the warps of a CTA within one instruction-cache window of the generated straight-line code
-#define SFB_LOCKSTEP() __syncthreads()
+#define SFB_LOCKSTEP(lo, hi) __syncthreads()
 
+#ifdef SFB_LOOP
+#include "sfb_step_loop.cuh"
+__device__ __forceinline__ void apply_role(const Ctx& c, int role) { loopk::apply_loop(c); }
+#else
 __device__ __forceinline__ void apply_role(const Ctx& c, int role) {
     const double2* __restrict__ yz = c.yz;
     const double2* __restrict__ yp = c.yp;
@@ -110,6 +114,7 @@ __device__ __forceinline__ void apply_role(const Ctx& c, int role) {
 #endif
 #include SFB_APPLY_INC
 }
+#endif
 
 #include "sfb_step_common.cuh"
 
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
 
     Ctx c;
     c.isA = (sb == 0);
-#ifdef SFB_GTAB
+#if defined(SFB_GTAB) || defined(SFB_LOOP)
     c.ktab = P.ktab;
 #else
     c.ktab = nullptr;
@@ -245,6 +250,9 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         attr_done[dev] = true;
     }
     SfbStepParams P = Pin;
+#ifdef SFB_LOOP
+    { void* tp = nullptr; e = cudaGetSymbolAddress(&tp, sfb_ltab); if (e != cudaSuccess) return e; P.ktab = reinterpret_cast<const double2*>(tp); }
+#endif
 #ifdef SFB_GTAB
     { void* tp = nullptr; e = cudaGetSymbolAddress(&tp, sfb_gtab); if (e != cudaSuccess) return e; P.ktab = reinterpret_cast<const double2*>(tp); }
 #endif

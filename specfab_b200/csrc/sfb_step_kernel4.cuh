@@ -102,7 +102,7 @@ __device__ __forceinline__ void row_out(const Ctx& c, double mine, double theirs
 #define SFB_ROW_OUT4(l, mu, m, t, z, q, r) row_out<l, mu>(c, m, t, z, q, r)
 #define SFB_N0_LOAD(l, mu) n0_load<l, mu>(c)
 #define SFB_ACC_LOAD(l, mu) acc_load<l, mu>(c)
-#define SFB_LOCKSTEP() __syncthreads()
+#define SFB_LOCKSTEP(lo, hi) __syncthreads()
 
 __device__ __forceinline__ void apply_all(const Ctx& c) {
     const double* __restrict__ yz = c.yz;

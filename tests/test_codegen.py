@@ -78,7 +78,7 @@ def test_physical_row_layout_is_a_bijection():
 def test_emitted_source_shape():
     body, tab, meta = es.emit(8, 1, 1, 64, "imm", True)
     assert body.count("SFB_ROW_OUT(") == 25          # canonical rows (l, mu>=0) at L=8
-    assert body.count("SFB_LOCKSTEP();") == 9
+    assert body.count("SFB_LOCKSTEP(") == 9
     assert meta["dfma_node"] == 2 * sum(meta["dfma_role"])
     body2, tab2, meta2 = es.emit(8, 1, 2, 32, "cbank", False)
     assert "sfb_tab[" in body2 and tab2.startswith("__constant__ double sfb_tab[")

@@ -50,7 +50,7 @@ def run(L, N, terms, scheme, variants, steps=10):
 
 
 if __name__ == "__main__":
-    V = list(range(0, 20))
+    V = list(range(0, 40))
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "8"):
         run(8, 1_000_000, ("lrot", "reg"), "rk4", V)
