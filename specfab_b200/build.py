@@ -31,26 +31,29 @@ ALL_L = [4, 6, 8, 10, 12, 14, 16, 18, 20]
 # variant 0 is the default; extra variants (EXTRA) are selectable with sfb_set_variant() for tuning runs
 EXTRA = {
     # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]
-    #   R = 0: four-lane kernel, R = -1: persistent four-lane kernel, R = -2: table-driven loop kernel
-    (8, 0): [(30, -2, 16, 6, "imm+ch2", False), (31, -2, 32, 3, "imm+ch2", False)],
-    (8, 1): [(30, -2, 16, 6, "imm+ch2", False), (31, -2, 32, 3, "imm+ch2", False), (32, -2, 64, 2, "imm+ch2", False)],
-    (12, 0): [(30, -2, 16, 6, "imm+ch2", False), (31, -2, 32, 3, "imm+ch2", False)],
-    (12, 1): [(30, -2, 16, 4, "imm+ch2", False), (31, -2, 32, 2, "imm+ch2", False), (32, -2, 16, 4, "imm+ch4", False), (33, -2, 48, 1, "imm+ch2", False)],
-    (20, 0): [(30, -2, 16, 3, "imm+ch2", False), (31, -2, 16, 3, "imm+ch4", False), (32, -2, 32, 1, "imm+ch2", False)],
-    (20, 1): [(30, -2, 16, 2, "imm+ch2", False), (31, -2, 16, 2, "imm+ch4", False), (32, -2, 32, 1, "imm+ch2", False)],
+    #   R >= 1: two-lane straight-line kernel with R warp roles; R = 0: four-lane straight-line kernel;
+    #   R = -1: persistent four-lane kernel (streaming TMA refill); R = -2: table-driven loop kernel (+rN roles, +chN rows/chunk)
+    (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False)],
+    (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False)],
+    (12, 0): [(1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
+    (12, 1): [(10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
+    (20, 0): [(1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],
+    (20, 1): [(1, 2, 16, 2, "imm", False), (20, -1, 32, 1, "imm", True), (30, -2, 16, 2, "imm+ch4+r6", False), (31, -2, 16, 2, "imm+ch2+r8", False)],
 }
-# default variant (0).  ncu (profiles/r01_notes.md): small tiles with several independent CTAs per SM hide the
-# per-tile load / prep phases; the DDRX kernels prefer four lanes per node (more threads per resident node).
+# default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
+#   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
+#   DDRX kernels up to L = 8 prefer four lanes per node;  L >= 12 with DDRX and every L >= 14: the table-driven loop kernel
+#   (straight-line code of 150 KB .. 1 MB per stage is instruction-fetch bound, profiles/r01_notes.md).
 TUNE = {
     (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
     (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
     (8, 0): (1, 16, 6, "imm", False), (8, 1): (0, 64, 2, "imm", True),
-    (10, 0): (0, 16, 4, "imm+w", True), (10, 1): (0, 32, 2, "imm", True),
-    (12, 0): (0, 16, 4, "imm+w", True), (12, 1): (0, 32, 2, "imm", True),
-    (14, 0): (2, 16, 3, "imm", False), (14, 1): (2, 16, 2, "imm", False),
-    (16, 0): (2, 16, 3, "imm", False), (16, 1): (2, 16, 2, "imm", False),
-    (18, 0): (2, 16, 3, "imm", False), (18, 1): (2, 16, 2, "imm", False),
-    (20, 0): (2, 16, 3, "imm", False), (20, 1): (2, 16, 2, "imm", False),
+    (10, 0): (0, 16, 4, "imm+w", True), (10, 1): (-2, 32, 2, "imm+ch2+r4", False),
+    (12, 0): (0, 16, 4, "imm+w", True), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
+    (14, 0): (-2, 16, 4, "imm+ch2+r4", False), (14, 1): (-2, 16, 3, "imm+ch2+r4", False),
+    (16, 0): (-2, 16, 4, "imm+ch2+r6", False), (16, 1): (-2, 16, 3, "imm+ch2+r6", False),
+    (18, 0): (-2, 16, 3, "imm+ch2+r6", False), (18, 1): (-2, 16, 2, "imm+ch2+r6", False),
+    (20, 0): (-2, 16, 3, "imm+ch2+r6", False), (20, 1): (-2, 16, 2, "imm+ch2+r6", False),
 }
 
 
@@ -87,7 +90,8 @@ def generate(Ls):
                     body = "// loop kernel: no generated body\n"
                     tab = "#define SFB_LOOP 1\n#define SFB_CH %d\n" % ch + tabsrc
                     skeleton = "sfb_step_kernel.cuh"
-                    R = 1
+                    R = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])     # warp roles per node group
+                    meta["R"] = R
                 elif R == -1:      # persistent, lock-stepped, streaming refill (four lanes per node)
                     body, tab, meta = emit_step.emit4(L, dd, TN, cm, True, window, mc, gd)
                     skeleton = "sfb_step_kernel5.cuh"

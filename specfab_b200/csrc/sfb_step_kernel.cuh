@@ -41,7 +41,8 @@ enum { SC_C0 = 0, SC_LAM = 1, SC_RM = 2, SC_G0 = 3, SC_TAUV = 4, SC_TSQV = 10, S
 
 struct Ctx {
     const double2 *yz, *yp, *yn;      // stage input planes (zero / positive / negative canonical m)
-    const double2* ktab;              // global table of operator entries (gtab mode)
+    const double2* ktab;              // global table of operator entries (gtab / loop mode)
+    double2* ring;                    // loop mode: this warp's private table ring in shared memory
     const double2* fz;                // forcing block of this lane set
     double2 *oz, *op;                 // next-stage buffer (rows owned by this lane: zero / positive plane)
     double2 *az, *ap;                 // RK accumulator buffer
@@ -102,8 +103,10 @@ __device__ __forceinline__ void row_out(const Ctx& c, double kr, double ki, doub
 
 #ifdef SFB_LOOP
 #include "sfb_step_loop.cuh"
-__device__ __forceinline__ void apply_role(const Ctx& c, int role) { loopk::apply_loop(c); }
+__device__ __forceinline__ void apply_role(const Ctx& c, int role) { loopk::apply_loop(c, role, kR, c.ring, (int)(threadIdx.x & 31)); }
+constexpr size_t kRingBytes = (size_t)(32 * (SFB_TN / 16) * SFB_R / 32) * 2 * (SFB_LT_PER_CHUNK / 2) * 16;
 #else
+constexpr size_t kRingBytes = 0;
 __device__ __forceinline__ void apply_role(const Ctx& c, int role) {
     const double2* __restrict__ yz = c.yz;
     const double2* __restrict__ yp = c.yp;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
     double2* forc = bufs + (size_t)nbuf * kNRow * kTN;
     double* scal = reinterpret_cast<double*>(forc + 2 * kNF * kTN);
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(scal + kNSc * kTN);
+    double2* rings = reinterpret_cast<double2*>(mbar + 2);          // loop mode: [warps][2][pairs per item]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = warp / kR, role = warp % kR;
@@ -156,6 +160,12 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
     }
+#ifdef SFB_LOOP
+    // the loop kernel reads columns unpredicated: the never-written twin rows of the m = 0 slots must be finite
+    for (int b = 0; b < nbuf; ++b)
+        for (int h = 0; h <= kL / 2; ++h)
+            for (int t = tid; t < kTN; t += kThreads) bufs[((size_t)b * kNRow + 2 * h * h + 1) * kTN + t] = make_double2(0.0, 0.0);
+#endif
     // ---- meanwhile: per-node forcing
     prep_tile(P, node0, nvalid, tid, forc, scal);
     {   // wait for the tile
@@ -169,6 +179,11 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
 
     Ctx c;
     c.isA = (sb == 0);
+#ifdef SFB_LOOP
+    c.ring = rings + (size_t)warp * 2 * (SFB_LT_PER_CHUNK / 2);
+#else
+    c.ring = nullptr;
+#endif
 #if defined(SFB_GTAB) || defined(SFB_LOOP)
     c.ktab = P.ktab;
 #else
@@ -235,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
 
 extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
     static bool attr_done[64] = {false};
-    const size_t fixed = (size_t)2 * kNF * kTN * 16 + (size_t)kNSc * kTN * 8 + 16;
+    const size_t fixed = (size_t)2 * kNF * kTN * 16 + (size_t)kNSc * kTN * 8 + 16 + kRingBytes;
     const size_t per_buf = (size_t)kNRow * kTN * 16;
     const size_t lim = 227 * 1024;
     const int nbuf_rk = SFB_HORNER ? 2 : 3;
