@@ -128,6 +128,18 @@ int sfb_M_REG_arr(const double* eps, int64_t N, double* M);
 int sfb_M_REG_arr_dev(const double* eps, int64_t N, int64_t ld, double* M, void* stream);
 int sfb_M_CDRX(double* M /* [nlm_len*nlm_len] */);
 
+/* apply_bounds(nlm): rescale the l=2 / l=4 blocks whose power spectrum exceeds the delta-function bound
+ *                                            src/specfabpy.f90:764-771, src/dynamics.f90:530-557 */
+int sfb_apply_bounds_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld);
+int sfb_apply_bounds_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out, void* stream);
+/* reduced form of real-valued ODFs: rnlm(N, rnlm_len) holds the m >= 0 coefficients, (L+2)^2/4 of them
+ *                                            src/specfabpy.f90:1039-1061, src/reducedform.f90:160-187 */
+int sfb_rnlm_len(void);
+int sfb_nlm_to_rnlm_arr(const double* nlm, double* rnlm, int64_t N);
+int sfb_nlm_to_rnlm_arr_dev(const double* nlm, double* rnlm, int64_t N, int64_t ld_nlm, int64_t ld_rnlm, void* stream);
+int sfb_rnlm_to_nlm_arr(const double* rnlm, double* nlm, int64_t N);
+int sfb_rnlm_to_nlm_arr_dev(const double* rnlm, double* nlm, int64_t N, int64_t ld_rnlm, int64_t ld_nlm, void* stream);
+
 /* tuning knob: select an alternative compiled kernel variant (0 = default); unknown ids fall back to 0 */
 int sfb_set_variant(int variant);
 

@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
-__all__ = ["M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
+__all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "Eij_eigenframe_arr", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
@@ -211,6 +211,56 @@ def nlm_LROT(nlm0, dt, Nt, D, W, iota):
         cur = step_arr(cur, (np.asarray(D[j]) + np.asarray(W[j]))[None], dt=dt, iota=iota, zeta=0.0, terms=("lrot",))
         out[j + 1] = cur[0]
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# bounds and reduced form, reference: src/specfabpy.f90:764-771, 1039-1061
+# ------------------------------------------------------------------------------------------
+
+def apply_bounds_arr(nlm):
+    n = _need_init()
+    x = _farr(nlm, np.complex128, (n,))
+    N = x.shape[0]
+    out = np.empty((N, n), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_apply_bounds_arr(x.ctypes.data, out.ctypes.data, N, N))
+    return out
+
+
+def apply_bounds(nlm):
+    """reference: src/specfabpy.f90:764-771"""
+    return np.ascontiguousarray(apply_bounds_arr(np.asarray(nlm)[None, :])[0])
+
+
+def rnlm_len():
+    return _lib.load().sfb_rnlm_len()
+
+
+def nlm_to_rnlm_arr(nlm):
+    n = _need_init()
+    x = _farr(nlm, np.complex128, (n,))
+    N = x.shape[0]
+    out = np.empty((N, rnlm_len()), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_nlm_to_rnlm_arr(x.ctypes.data, out.ctypes.data, N))
+    return out
+
+
+def rnlm_to_nlm_arr(rnlm):
+    n = _need_init()
+    x = _farr(rnlm, np.complex128, (rnlm_len(),))
+    N = x.shape[0]
+    out = np.empty((N, n), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_rnlm_to_nlm_arr(x.ctypes.data, out.ctypes.data, N))
+    return out
+
+
+def nlm_to_rnlm(nlm, rnlm_len_=None):
+    """reference: src/specfabpy.f90:1046-1053"""
+    return np.ascontiguousarray(nlm_to_rnlm_arr(np.asarray(nlm)[None, :])[0])
+
+
+def rnlm_to_nlm(rnlm, nlm_len_=None):
+    """reference: src/specfabpy.f90:1055-1061"""
+    return np.ascontiguousarray(rnlm_to_nlm_arr(np.asarray(rnlm)[None, :])[0])
 
 
 # ------------------------------------------------------------------------------------------

@@ -61,6 +61,13 @@ SIGNATURES = {
     "sfb_M_REG_arr": (C.c_int, [_P, _I64, _P]),
     "sfb_M_REG_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "sfb_M_CDRX": (C.c_int, [_P]),
+    "sfb_apply_bounds_arr": (C.c_int, [_P, _P, _I64, _I64]),
+    "sfb_apply_bounds_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P]),
+    "sfb_rnlm_len": (C.c_int, []),
+    "sfb_nlm_to_rnlm_arr": (C.c_int, [_P, _P, _I64]),
+    "sfb_nlm_to_rnlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P]),
+    "sfb_rnlm_to_nlm_arr": (C.c_int, [_P, _P, _I64]),
+    "sfb_rnlm_to_nlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "sfb_set_variant": (C.c_int, [C.c_int]),
     "sfb_dev_malloc": (C.c_int, [C.POINTER(_P), _I64]),
     "sfb_dev_free": (C.c_int, [_P]),

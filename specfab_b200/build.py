@@ -33,8 +33,11 @@ EXTRA = {
     # (L, ddrx): [(variant id, R, TN, MINB, const_mode, sync)]
     #   R >= 1: two-lane straight-line kernel with R warp roles; R = 0: four-lane straight-line kernel;
     #   R = -1: persistent four-lane kernel (streaming TMA refill); R = -2: table-driven loop kernel (+rN roles, +chN rows/chunk)
-    (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False)],
-    (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False)],
+    (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
+             (11, 0, 16, 7, "imm+w", False), (12, 0, 32, 4, "imm+w", False), (13, 1, 16, 7, "imm", False), (14, 1, 16, 8, "imm", False)],
+    (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
+             (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
+             (15, 0, 48, 3, "imm", False), (16, 0, 32, 5, "imm", False)],
     (12, 0): [(1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
     (12, 1): [(10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
     (20, 0): [(1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],
@@ -47,7 +50,7 @@ EXTRA = {
 TUNE = {
     (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
     (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
-    (8, 0): (1, 16, 6, "imm", False), (8, 1): (0, 64, 2, "imm", True),
+    (8, 0): (1, 16, 6, "imm", False), (8, 1): (0, 64, 2, "imm", False),
     (10, 0): (0, 16, 4, "imm+w", True), (10, 1): (-2, 32, 2, "imm+ch2+r4", False),
     (12, 0): (0, 16, 4, "imm+w", True), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
     (14, 0): (-2, 16, 4, "imm+ch2+r4", False), (14, 1): (-2, 16, 3, "imm+ch2+r4", False),

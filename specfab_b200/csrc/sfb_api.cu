@@ -14,6 +14,9 @@ cudaError_t sfb_launch_mexport(int mode, int L, const double* a33, const double*
                                long long N, long long ld, double iota, double zeta, double2* M, cudaStream_t st);
 cudaError_t sfb_launch_mreg(int L, const SfbRegConst& reg, const double* eps, long long N, long long ld, double* M, cudaStream_t st);
 void sfb_ops_release();
+cudaError_t sfb_launch_bounds(const double2* in, double2* out, long long N, long long ldi, long long ldo, int n, cudaStream_t st);
+cudaError_t sfb_launch_reduced(int to_reduced, const double2* src, double2* dst, long long N, long long lds, long long ldd, int L,
+                               cudaStream_t st);
 cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
@@ -544,6 +547,62 @@ int sfb_M_CDRX(double* M) {      // constant operator diag(-l(l+1)), src/dynamic
         for (int m = -l; m <= l; ++m, ++j) M[(size_t)j * g.n + j] = -(double)(l * (l + 1));
     return SFB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// apply_bounds, reduced form
+// ---------------------------------------------------------------------------------------------
+int sfb_rnlm_len(void) { return g.L ? (g.L + 2) * (g.L + 2) / 4 : 0; }          // src/reducedform.f90:26
+
+int sfb_apply_bounds_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out, void* stream) {
+    int rc = basic_check(nlm_in, N, ld_in);
+    if (rc) return rc;
+    if (ld_out < N || (N && !nlm_out)) return fail(SFB_EINVAL, "bad output");
+    CK(sfb_launch_bounds(reinterpret_cast<const double2*>(nlm_in), reinterpret_cast<double2*>(nlm_out), N, ld_in, ld_out, g.n, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_apply_bounds_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld) {
+    int rc = basic_check(nlm_in, N, ld);
+    if (rc || N == 0) return rc;
+    if (!nlm_out) return fail(SFB_EINVAL, "null output");
+    DevTmp in;                      // only the l <= 4 rows change: stage 15 rows, rescale in place, copy them back
+    if ((rc = stage_rows(in, nlm_in, N, ld, 15))) return rc;
+    CK(sfb_launch_bounds(in.as<double2>(), in.as<double2>(), N, N, N, 15, nullptr));
+    if (nlm_out != nlm_in) {
+        for (int j = 15; j < g.n; ++j) memcpy(nlm_out + 2 * (size_t)j * ld, nlm_in + 2 * (size_t)j * ld, (size_t)N * 16);
+    }
+    CK(cudaMemcpy2D(nlm_out, (size_t)ld * 16, in.p, (size_t)N * 16, (size_t)N * 16, 15, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_nlm_to_rnlm_arr_dev(const double* nlm, double* rnlm, int64_t N, int64_t ld_nlm, int64_t ld_rnlm, void* stream) {
+    int rc = basic_check(nlm, N, ld_nlm);
+    if (rc) return rc;
+    if (ld_rnlm < N || (N && !rnlm)) return fail(SFB_EINVAL, "bad output");
+    CK(sfb_launch_reduced(1, reinterpret_cast<const double2*>(nlm), reinterpret_cast<double2*>(rnlm), N, ld_nlm, ld_rnlm, g.L, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_rnlm_to_nlm_arr_dev(const double* rnlm, double* nlm, int64_t N, int64_t ld_rnlm, int64_t ld_nlm, void* stream) {
+    int rc = basic_check(rnlm, N, ld_rnlm);
+    if (rc) return rc;
+    if (ld_nlm < N || (N && !nlm)) return fail(SFB_EINVAL, "bad output");
+    CK(sfb_launch_reduced(0, reinterpret_cast<const double2*>(rnlm), reinterpret_cast<double2*>(nlm), N, ld_rnlm, ld_nlm, g.L, (cudaStream_t)stream));
+    return SFB_OK;
+}
+static int reduced_host(int to_reduced, const double* src, double* dst, int64_t N) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (N == 0) return SFB_OK;
+    if (!src || !dst) return fail(SFB_EINVAL, "null array");
+    const size_t nr = (size_t)sfb_rnlm_len(), ns = to_reduced ? (size_t)g.n : nr, nd = to_reduced ? nr : (size_t)g.n;
+    DevTmp a, b;
+    CK(a.alloc(ns * N * 16));
+    CK(b.alloc(nd * N * 16));
+    CK(cudaMemcpy(a.p, src, ns * N * 16, cudaMemcpyHostToDevice));
+    CK(sfb_launch_reduced(to_reduced, a.as<double2>(), b.as<double2>(), N, N, N, g.L, nullptr));
+    CK(cudaMemcpy(dst, b.p, nd * N * 16, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_nlm_to_rnlm_arr(const double* nlm, double* rnlm, int64_t N) { return reduced_host(1, nlm, rnlm, N); }
+int sfb_rnlm_to_nlm_arr(const double* rnlm, double* nlm, int64_t N) { return reduced_host(0, rnlm, nlm, N); }
 
 int sfb_dev_malloc(void** p, int64_t bytes) {
     if (!p || bytes < 0) return fail(SFB_EINVAL, "bad args");

@@ -133,6 +133,53 @@ __global__ void __launch_bounds__(kBlock) eij_kernel(const double2* __restrict__
     if (status) status[p] = st;
 }
 
+// apply_bounds (src/dynamics.f90:530-557): rescale the l=2 / l=4 blocks if their power spectrum S(l)
+// (src/idealstate.f90:80-93) exceeds that of the delta function; other coefficients pass through.
+__global__ void __launch_bounds__(kBlock) bounds_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long N,
+                                                        long long ldi, long long ldo, int n) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double2 v[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) v[j] = in[(long long)j * ldi + p];
+    const double S0 = v[0].x * v[0].x;                      // real(nlm(1))**2
+    double s2 = 0.0, s4 = 0.0;
+#pragma unroll
+    for (int j = 1; j < 6; ++j) s2 += v[j].x * v[j].x + v[j].y * v[j].y;
+#pragma unroll
+    for (int j = 6; j < 15; ++j) s4 += v[j].x * v[j].x + v[j].y * v[j].y;
+    const double S2_rel = (1.0 / 5 * s2) / S0, S4_rel = (1.0 / 9 * s4) / S0;
+    const double f2 = S2_rel > 1.0 ? sqrt(S2_rel) : 1.0, f4 = S4_rel > 1.0 ? sqrt(S4_rel) : 1.0;
+    out[p] = v[0];
+#pragma unroll
+    for (int j = 1; j < 6; ++j) out[(long long)j * ldo + p] = S2_rel > 1.0 ? make_double2(v[j].x / f2, v[j].y / f2) : v[j];
+#pragma unroll
+    for (int j = 6; j < 15; ++j) out[(long long)j * ldo + p] = S4_rel > 1.0 ? make_double2(v[j].x / f4, v[j].y / f4) : v[j];
+    if (in != out)
+        for (int j = 15; j < n; ++j) out[(long long)j * ldo + p] = in[(long long)j * ldi + p];
+}
+
+// nlm <-> rnlm (src/reducedform.f90:160-187).  rnlm rows are the m >= 0 coefficients in (l, m=0..l) order;
+// rnlm_to_nlm fills n_l^{-m} = (-1)^m conj(n_l^m).  blockIdx.y = full-form row j.
+__global__ void __launch_bounds__(kBlock) reduced_kernel(int to_reduced, const double2* __restrict__ src, double2* __restrict__ dst,
+                                                         long long N, long long lds, long long ldd, int L) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    const int j = blockIdx.y;                                // full-form row
+    int l = 0;
+    while ((l + 2) * (l + 3) / 2 - (l + 2) <= j) l += 2;
+    const int m = j - l * (l + 1) / 2;
+    const int am = m < 0 ? -m : m;
+    const int r = (l / 2) * (l / 2) + am;                    // reduced row of (l, |m|): sum_{l'<l}(l'+1) + |m| = (l/2)^2 + |m|
+    if (to_reduced) {
+        if (m >= 0) dst[(long long)r * ldd + p] = src[(long long)j * lds + p];
+    } else {
+        double2 v = src[(long long)r * lds + p];
+        if (m < 0) { v.y = -v.y; if (am & 1) { v.x = -v.x; v.y = -v.y; } }
+        dst[(long long)j * ldd + p] = v;
+    }
+}
+
 inline unsigned nblk(long long N) { return (unsigned)((N + kBlock - 1) / kBlock); }
 
 }  // namespace
@@ -154,5 +201,16 @@ cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const 
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
                            int* status, cudaStream_t st) {
     if (N > 0) eij_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+    return cudaGetLastError();
+}
+
+cudaError_t sfb_launch_bounds(const double2* in, double2* out, long long N, long long ldi, long long ldo, int n, cudaStream_t st) {
+    if (N > 0) bounds_kernel<<<nblk(N), kBlock, 0, st>>>(in, out, N, ldi, ldo, n);
+    return cudaGetLastError();
+}
+cudaError_t sfb_launch_reduced(int to_reduced, const double2* src, double2* dst, long long N, long long lds, long long ldd, int L,
+                               cudaStream_t st) {
+    const int n = (L + 1) * (L + 2) / 2;
+    if (N > 0) reduced_kernel<<<dim3(nblk(N), n), kBlock, 0, st>>>(to_reduced, src, dst, N, lds, ldd, L);
     return cudaGetLastError();
 }

@@ -190,3 +190,24 @@ def test_moments_after_1000_steps():
     E, ei, lami = sf.Eij_eigenframe_arr(got, GRAIN, ALPHA, 1, return_frame=True)
     Er = np.array([orc.Eij_tranisotropic(ref[p], ei[p, 0], ei[p, 1], ei[p, 2], GRAIN, ALPHA, 1) for p in range(N)])
     assert np.abs(E / Er - 1).max() < 1e-9
+
+
+def test_apply_bounds_and_reduced_form():
+    """src/dynamics.f90:530-557 and src/reducedform.f90:160-187"""
+    import specfab_b200 as sf
+    lm, n = sf.init(L)
+    orc.init(L)
+    x = random_states(L, 30, 71, True, decay=1.0) * 3       # strong fabrics: several exceed the delta-function spectrum
+    x[:, 0] = 1 / np.sqrt(4 * np.pi)
+    got = sf.apply_bounds_arr(x)
+    ref = np.array([orc.apply_bounds(v) for v in x])
+    assert np.abs(got - ref).max() < 1e-14 and (np.abs(ref - x).max(axis=1) > 1e-3).sum() > 3
+    assert np.array_equal(sf.apply_bounds(x[2]), got[2])
+    # reduced form: m >= 0 coefficients in (l, m) order; the round trip reproduces physical states exactly
+    r = sf.nlm_to_rnlm_arr(x)
+    assert r.shape == (30, sf.rnlm_len()) and sf.rnlm_len() == (L + 2) ** 2 // 4
+    keep = [j for j in range(n) if lm[1, j] >= 0]
+    assert np.array_equal(r, x[:, keep])
+    back = sf.rnlm_to_nlm_arr(r)
+    assert np.abs(back - x).max() < 1e-16
+    assert np.array_equal(sf.rnlm_to_nlm(sf.nlm_to_rnlm(x[1])), back[1])
