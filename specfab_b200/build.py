@@ -34,14 +34,19 @@ EXTRA = {
     #   R >= 1: two-lane straight-line kernel with R warp roles; R = 0: four-lane straight-line kernel;
     #   R = -1: persistent four-lane kernel (streaming TMA refill); R = -2: table-driven loop kernel (+rN roles, +chN rows/chunk)
     (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
-             (11, 0, 16, 7, "imm+w", False), (12, 0, 32, 4, "imm+w", False), (13, 1, 16, 7, "imm", False), (14, 1, 16, 8, "imm", False)],
+             (11, 2, 16, 7, "imm", False), (12, 2, 16, 6, "imm", False), (13, 2, 16, 5, "imm", False), (14, 2, 32, 3, "imm", False),
+             (15, 3, 16, 7, "imm", False), (16, 2, 16, 7, "imm+c6", False)],
     (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
-             (15, 0, 48, 3, "imm", False), (16, 0, 32, 5, "imm", False)],
-    (12, 0): [(1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
-    (12, 1): [(10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
-    (20, 0): [(1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],
-    (20, 1): [(1, 2, 16, 2, "imm", False), (20, -1, 32, 1, "imm", True), (30, -2, 16, 2, "imm+ch4+r6", False), (31, -2, 16, 2, "imm+ch2+r8", False)],
+             (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False)],
+    (12, 0): [(2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
+              (1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
+    (12, 1): [(2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
+              (10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
+    (20, 0): [(2, 5, 16, 3, "imm", False), (3, 4, 16, 3, "imm", False), (4, 7, 16, 2, "imm", False),
+              (1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],
+    (20, 1): [(2, 8, 16, 2, "imm", False), (3, 6, 16, 2, "imm", False), (4, 4, 16, 2, "imm", False), (5, 10, 16, 2, "imm", False),
+              (1, 2, 16, 2, "imm", False), (20, -1, 32, 1, "imm", True), (30, -2, 16, 2, "imm+ch4+r6", False), (31, -2, 16, 2, "imm+ch2+r8", False)],
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
