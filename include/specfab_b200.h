@@ -110,6 +110,20 @@ int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const doubl
 int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
                                double* Eij, double* ei, double* lami, int32_t* status, void* stream);
 
+/* Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3 (N,nlm_len), e1,e2,e3 (N,3), Eij_grain(6), alpha, n_grain) -> Eij(N,6)
+ *                                            src/specfabpy.f90:488-500, src/enhancementfactors.f90:134-189.
+ * Orthotropic grains (olivine): nlm_1..3 are the distributions of the slip-system axes (b, n, v); where
+ * REAL(nlm_3(1)) <= 1e-8 (or nlm_3 == NULL) the third axis is derived from the first two
+ * (src/moments.f90:357-384).  Eij_grain = (Ebb, Enn, Evv, Env, Ebv, Enb).  Like the reference only the Sachs
+ * bound is evaluated (alpha is ignored) and only n_grain = 1 is supported: any other n_grain yields NaN, the
+ * reference's 0/0 (src/homogenizations.f90:316-318).  Each state has its own leading dimension. */
+int sfb_Eij_orthotropic_arr(const double* nlm_1, const double* nlm_2, const double* nlm_3, int64_t N, int64_t ld,
+                            const double* e1, const double* e2, const double* e3,
+                            const double* Eij_grain, double alpha, int n_grain, double* Eij);
+int sfb_Eij_orthotropic_arr_dev(const double* nlm_1, int64_t ld1, const double* nlm_2, int64_t ld2, const double* nlm_3, int64_t ld3,
+                                int64_t N, const double* e1, const double* e2, const double* e3,
+                                const double* Eij_grain, double alpha, int n_grain, double* Eij, void* stream);
+
 /* Batched operator export (the form the Eulerian FE couplers consume: src/specfabpy/fenics/CPO.py:200-202,
  * src/specfabpy/firedrake/ice.py:202-204).  M is (N, nlm_len, nlm_len) in Fortran order, complex(8) for
  * M_LROT / M_DDRX(_src), real(8) for M_REG.  eps, omg, tau: (N,3,3).

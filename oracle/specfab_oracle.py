@@ -663,3 +663,130 @@ def nlm_LROT(nlm0, dt, Nt, D, W, iota):
     for j in range(Nt - 1):
         out[j + 1] = out[j] + dt * (M_LROT(D[j], W[j], iota, 0.0) @ out[j])
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Orthotropic grains: Eij_orthotropic  (src/enhancementfactors.f90:134-189)
+# ---------------------------------------------------------------------------------------------
+# The four moment bodies are 80-200 KB of generated bilinear forms with real(4) constants; they are NOT
+# transcribed by hand: tools/make_orthotropic_tables.py interprets the reference text once (symbolically,
+# Fortran kind semantics) and stores the coefficient tensors in specfab_b200/data/orthotropic_l4.npz.
+# tests/golden/refbodies.npz (numeric interpretation of the same text) pins them.
+
+_ORTH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "specfab_b200", "data", "orthotropic_l4.npz")
+_orth_cache = {}
+
+
+def _orth_tables():
+    if not _orth_cache:
+        d = np.load(_ORTH)
+        for tag in ("v2", "v4", "c2b2", "c2v2"):
+            _orth_cache[tag] = {k: d["%s_%s" % (tag, k)] for k in ("e", "p", "q", "c", "norm_p", "norm_q", "norm_c", "k", "rank")}
+    return _orth_cache
+
+
+def _bilinear(tag, blm, nlm):
+    """ev = REAL(sum C b_p n_q) * k / norm   (src/moments.f90:242-311 with the include bodies)"""
+    T = _orth_tables()[tag]
+    b = np.zeros(15, dtype=np.complex128); n = np.zeros(15, dtype=np.complex128)
+    bl = np.asarray(blm, dtype=np.complex128)[:15]; nl = np.asarray(nlm, dtype=np.complex128)[:15]
+    b[:bl.size] = bl; n[:nl.size] = nl
+    rank = int(T["rank"])
+    ev = np.zeros(3 ** rank)
+    np.add.at(ev, T["e"], (T["c"] * b[T["p"]] * n[T["q"]]).real)
+    norm = float(np.sum((T["norm_c"] * b[T["norm_p"]] * n[T["norm_q"]]).real))
+    return (ev * float(T["k"]) / norm).reshape((3,) * rank, order="F")
+
+
+def a2_orth(blm, nlm):
+    """src/moments.f90:242-258 + include/ev_v2__body.f90"""
+    return _bilinear("v2", blm, nlm)
+
+
+def a4_orth(blm, nlm):
+    """src/moments.f90:260-276 + include/ev_v4__body.f90"""
+    return _bilinear("v4", blm, nlm)
+
+
+def a4_joint(blm, nlm):
+    """src/moments.f90:278-293 + include/ev_c2b2__body.f90"""
+    return _bilinear("c2b2", blm, nlm)
+
+
+def a4_jointcross(blm, nlm):
+    """src/moments.f90:295-311 + include/ev_c2v2__body.f90"""
+    return _bilinear("c2v2", blm, nlm)
+
+
+def ai_orthotropic(q1, q2, q3):
+    """src/moments.f90:357-384 -> (a2_i[3], a4_ii[3], a4_jk[3])"""
+    a2_i = [a2(q1), a2(q2), None]
+    a4_ii = [a4(q1), a4(q2), None]
+    a4_jk = [None, None, a4_joint(q1, q2)]
+    if np.asarray(q3)[0].real > _r4(1e-8):
+        a2_i[2] = a2(q3); a4_ii[2] = a4(q3)
+        a4_jk[0] = a4_joint(q2, q3); a4_jk[1] = a4_joint(q1, q3)
+    else:
+        a2_i[2] = a2_orth(q1, q2); a4_ii[2] = a4_orth(q1, q2)
+        a4_jk[0] = a4_jointcross(q2, q1); a4_jk[1] = a4_jointcross(q1, q2)
+    return a2_i, a4_ii, a4_jk
+
+
+def rheo_params_orthotropic(Eij, n):
+    """src/rheologies.f90:186-206 -> (lami[6], gam)"""
+    B = [math.pow(x, 2 / (n + 1)) for x in Eij]
+    lami = [-B[0] + B[1] + B[2], +B[0] - B[1] + B[2], +B[0] + B[1] - B[2], B[3], B[4], B[5]]
+    gam = 2 * B[0] * B[1] + 2 * B[0] * B[2] + 2 * B[1] * B[2] - B[0] ** 2 - B[1] ** 2 - B[2] ** 2
+    return lami, gam
+
+
+def a4_sym2(a):
+    """src/tensorproducts.f90:53-64: X(j,k,:,:) = (a(j,k,:,:) + a(:,:,j,k))/2"""
+    return (a + a.transpose(2, 3, 0, 1)) / 2
+
+
+def a4_sym4(a):
+    """src/tensorproducts.f90:66-82: X(i,j,k,l) = (a(i,k,j,l) + a(k,j,i,l) + a(i,l,k,j) + a(l,j,k,i))/4"""
+    return (a.transpose(0, 2, 1, 3) + a.transpose(2, 1, 0, 3) + a.transpose(0, 3, 2, 1) + a.transpose(3, 1, 2, 0)) / 4
+
+
+def _check_sym4():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 3, 3, 3))
+    X = a4_sym4(a)
+    i, j, k, l = 0, 1, 2, 1
+    assert abs(X[i, j, k, l] - (a[i, k, j, l] + a[k, j, i, l] + a[i, l, k, j] + a[l, j, k, i]) / 4) < 1e-15
+
+
+def rheo_fwd_orthotropic_sachshomo(tau, a2_i, a4_ii, a4_jk, Eij_grain, n_grain):
+    """src/homogenizations.f90:288-319"""
+    lami, gam = rheo_params_orthotropic(Eij_grain, float(n_grain))
+    ci = [4.0 / 3 * x for x in lami[:3]] + [2 * x for x in lami[3:]]
+    ji, ki = [1, 2, 0], [2, 0, 1]
+    M2 = [(a4_ii[ji[i]] + a4_ii[ki[i]] - 2 * a4_sym2(a4_jk[i])) / 4 for i in range(3)]
+    H2 = [a4_sym4(a4_jk[i]) for i in range(3)]
+    if n_grain != 1:
+        return np.zeros((3, 3))           # "n_grain not supported, silently return 0"
+    Q = ci[0] * M2[0] + ci[1] * M2[1] + ci[2] * M2[2] + ci[3] * H2[0] + ci[4] * H2[1] + ci[5] * H2[2]
+    tau = np.asarray(tau, dtype=np.float64)
+    # doubleinner42: eps(l,k) = sum_ij Q(l,k,i,j) tau(j,i)     src/tensorproducts.f90:171-181
+    return np.einsum("lkij,ji->lk", Q, tau)
+
+
+def Evw_orthotropic(v, w, tau, q1, q2, q3, Eij_grain, alpha, n_grain):
+    """src/enhancementfactors.f90:158-189 (Sachs only)"""
+    vw = np.outer(v, w)
+    q1 = np.asarray(q1, dtype=np.complex128)
+    qiso = np.zeros_like(q1); qiso[0] = q1[0]
+    A = ai_orthotropic(q1, q2, q3)
+    Aiso = ai_orthotropic(qiso, qiso, qiso)
+    with np.errstate(all="ignore"):      # IEEE division like the compiled reference (0/0 -> NaN for n_grain /= 1)
+        return float(np.float64(doubleinner22(rheo_fwd_orthotropic_sachshomo(tau, *A, Eij_grain, n_grain), vw)) /
+                     np.float64(doubleinner22(rheo_fwd_orthotropic_sachshomo(tau, *Aiso, Eij_grain, n_grain), vw)))
+
+
+def Eij_orthotropic(q1, q2, q3, e1, e2, e3, Eij_grain, alpha, n_grain):
+    """src/enhancementfactors.f90:134-156 -> (E11,E22,E33,E23,E13,E12)"""
+    args = [(e1, e1, tau_vv(e1)), (e2, e2, tau_vv(e2)), (e3, e3, tau_vv(e3)),
+            (e2, e3, tau_vw(e2, e3)), (e1, e3, tau_vw(e1, e3)), (e1, e2, tau_vw(e1, e2))]
+    return np.array([Evw_orthotropic(v, w, t, q1, q2, q3, Eij_grain, alpha, n_grain) for v, w, t in args])

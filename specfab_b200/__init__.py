@@ -21,7 +21,7 @@ from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, Sp
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
-           "Eij_eigenframe_arr", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
+           "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
 
 _state = {"L": None, "n": None}
@@ -334,6 +334,26 @@ def Eij_tranisotropic_arr(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_sta
     return (out, st) if return_status else out
 
 
+def Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij_grain, alpha, n_grain):
+    """Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3 (N,nlm_len), e1,e2,e3 (N,3), Eij_grain(6), alpha, n_grain) -> Eij (N,6)
+    reference: src/specfabpy.f90:488-500.  Pass nlm_3 = 0*nlm_1 (or None) to derive the third axis from the first two."""
+    _need_init()
+    x1, x2 = _nlm15(nlm_1), _nlm15(nlm_2)
+    x3 = _nlm15(nlm_3) if nlm_3 is not None else None
+    N = x1.shape[0]
+    if x2.shape[0] != N or (x3 is not None and x3.shape[0] != N):
+        raise ValueError("nlm_1, nlm_2, nlm_3 must have the same number of nodes")
+    es = [_farr(e, np.float64, (3,)) for e in (e1, e2, e3)]
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    if g.shape != (6,):
+        raise ValueError("Eij_grain must have 6 entries (Ebb, Enn, Evv, Env, Ebv, Enb)")
+    out = np.empty((N, 6), dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_Eij_orthotropic_arr(x1.ctypes.data, x2.ctypes.data, x3.ctypes.data if x3 is not None else None, N, N,
+                                                   es[0].ctypes.data, es[1].ctypes.data, es[2].ctypes.data,
+                                                   g.ctypes.data, float(alpha), int(n_grain), out.ctypes.data))
+    return out
+
+
 def Eij_eigenframe_arr(nlm, Eij_grain, alpha, n_grain, return_frame=False, return_status=False):
     """Fused a2 -> eigenframe -> Eij_tranisotropic (eigenenhancements) of every node -> Eij (N,6)
     [, ei (N,3,3), lami (N,3)] [, status].  Batches src/specfabpy/fenics/enhancementfactor.py:101-128."""
@@ -370,6 +390,12 @@ def eig(nlm):
     """reference: src/specfabpy.f90:312-320 -> (ei[3,3], lami[3])"""
     ei, lami = eig_arr(np.asarray(nlm)[None, :])
     return np.ascontiguousarray(ei[0]), np.ascontiguousarray(lami[0])
+
+
+def Eij_orthotropic(nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij_grain, alpha, n_grain):
+    """reference: src/specfabpy.f90:436-446 -> Eij[6]"""
+    one = lambda v: np.asarray(v)[None, :]
+    return np.ascontiguousarray(Eij_orthotropic_arr(one(nlm_1), one(nlm_2), one(nlm_3), one(e1), one(e2), one(e3), Eij_grain, alpha, n_grain)[0])
 
 
 def Eij_tranisotropic(nlm, e1, e2, e3, Eij_grain, alpha, n_grain):
@@ -452,6 +478,24 @@ def Eij_tranisotropic_arr_dev(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, out=No
     _lib.check(_lib.load().sfb_Eij_tranisotropic_arr_dev(nlm.data_ptr(), N, N, e1.data_ptr(), e2.data_ptr(), e3.data_ptr(), g.ctypes.data,
                                                          float(alpha), int(n_grain), out.data_ptr(),
                                                          status.data_ptr() if status is not None else None, _stream_ptr()))
+    return out
+
+
+def Eij_orthotropic_arr_dev(nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij_grain, alpha, n_grain, out=None):
+    """Eij of orthotropic grains on resident states: nlm_i (nlm_len,N) complex128 CUDA (nlm_3 may be None),
+    e1/e2/e3 (3,N) float64 CUDA -> (6,N)."""
+    import torch
+    _need_init()
+    N = nlm_1.shape[1]
+    if out is None:
+        out = torch.empty((6, N), dtype=torch.float64, device=nlm_1.device)
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    if g.shape != (6,):
+        raise ValueError("Eij_grain must have 6 entries (Ebb, Enn, Evv, Env, Ebv, Enb)")
+    _lib.check(_lib.load().sfb_Eij_orthotropic_arr_dev(nlm_1.data_ptr(), N, nlm_2.data_ptr(), N,
+                                                       nlm_3.data_ptr() if nlm_3 is not None else None, N, N,
+                                                       e1.data_ptr(), e2.data_ptr(), e3.data_ptr(), g.ctypes.data,
+                                                       float(alpha), int(n_grain), out.data_ptr(), _stream_ptr()))
     return out
 
 

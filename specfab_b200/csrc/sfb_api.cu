@@ -21,6 +21,9 @@ cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double*
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
                            long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2* q2, long long ld2, const double2* q3, long long ld3,
+                                long long N, const double* e1, const double* e2, const double* e3, long long lde,
+                                const double* Eij_grain, int n_grain, double* Eij, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
                            int* status, cudaStream_t st);
@@ -425,6 +428,46 @@ int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const do
     if (rc) return rc;
     CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
     if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_Eij_orthotropic_arr_dev(const double* nlm_1, int64_t ld1, const double* nlm_2, int64_t ld2, const double* nlm_3, int64_t ld3,
+                                int64_t N, const double* e1, const double* e2, const double* e3,
+                                const double* Eij_grain, double alpha, int n_grain, double* Eij, void* stream) {
+    (void)alpha;   // Sachs only, src/enhancementfactors.f90:160-162
+    int rc = basic_check(nlm_1, N, ld1);
+    if (rc) return rc;
+    if ((rc = basic_check(nlm_2, N, ld2))) return rc;
+    if (nlm_3 && ld3 < N) return fail(SFB_EINVAL, "need N <= ld3");
+    if (!Eij_grain) return fail(SFB_EINVAL, "null Eij_grain");
+    if (N == 0) return SFB_OK;
+    if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_eij_orth(reinterpret_cast<const double2*>(nlm_1), ld1, reinterpret_cast<const double2*>(nlm_2), ld2,
+                           reinterpret_cast<const double2*>(nlm_3), ld3, N, e1, e2, e3, N, Eij_grain, n_grain, Eij, N, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_Eij_orthotropic_arr(const double* nlm_1, const double* nlm_2, const double* nlm_3, int64_t N, int64_t ld,
+                            const double* e1, const double* e2, const double* e3,
+                            const double* Eij_grain, double alpha, int n_grain, double* Eij) {
+    int rc = basic_check(nlm_1, N, ld);
+    if (rc) return rc;
+    if ((rc = basic_check(nlm_2, N, ld))) return rc;
+    if (!Eij_grain) return fail(SFB_EINVAL, "null Eij_grain");
+    if (N == 0) return SFB_OK;
+    if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
+    DevTmp q1, q2, q3, de, out;
+    if ((rc = stage_rows(q1, nlm_1, N, ld, 15))) return rc;
+    if ((rc = stage_rows(q2, nlm_2, N, ld, 15))) return rc;
+    if (nlm_3 && (rc = stage_rows(q3, nlm_3, N, ld, 15))) return rc;
+    CK(de.alloc((size_t)N * 9 * 8));
+    CK(cudaMemcpy(de.as<double>(), e1, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(de.as<double>() + 3 * N, e2, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(de.as<double>() + 6 * N, e3, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(out.alloc((size_t)N * 6 * 8));
+    rc = sfb_Eij_orthotropic_arr_dev(q1.as<double>(), N, q2.as<double>(), N, nlm_3 ? q3.as<double>() : nullptr, N, N,
+                                     de.as<double>(), de.as<double>() + 3 * N, de.as<double>() + 6 * N, Eij_grain, alpha, n_grain,
+                                     out.as<double>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }
 int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,

@@ -211,3 +211,73 @@ def test_apply_bounds_and_reduced_form():
     back = sf.rnlm_to_nlm_arr(r)
     assert np.abs(back - x).max() < 1e-16
     assert np.array_equal(sf.rnlm_to_nlm(sf.nlm_to_rnlm(x[1])), back[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# Orthotropic grains (olivine): Eij_orthotropic_arr      src/specfabpy.f90:488-500
+# ---------------------------------------------------------------------------------------------
+OLIVINE = (1.0, 1.0, 1.0, 1.0, 1.0, 10.0)      # (Ebb, Enn, Evv, Env, Ebv, Enb): easy b-n slip system
+
+
+def _frames(N, seed):
+    rng = np.random.default_rng(seed)
+    Q = np.linalg.qr(rng.standard_normal((N, 3, 3)))[0]
+    return Q[:, :, 0].copy(), Q[:, :, 1].copy(), Q[:, :, 2].copy()
+
+
+@pytest.mark.parametrize("third", ["derived", "given", "mixed", "null"])
+def test_Eij_orthotropic_parity(third):
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    N = 37                      # not a multiple of the CTA's node tile
+    q1 = random_states(L, N, 31, True, decay=0.35)
+    q2 = random_states(L, N, 32, True, decay=0.35)
+    q3 = random_states(L, N, 33, True, decay=0.35)
+    if third == "derived":
+        q3 = 0 * q3
+    elif third == "mixed":
+        q3[::3] = 0
+    e1, e2, e3 = _frames(N, 34)
+    E = sf.Eij_orthotropic_arr(q1, q2, None if third == "null" else q3, e1, e2, e3, OLIVINE, 0.0, 1)
+    q3r = 0 * q1 if third == "null" else q3
+    ref = np.array([orc.Eij_orthotropic(q1[p], q2[p], q3r[p], e1[p], e2[p], e3[p], OLIVINE, 0.0, 1) for p in range(N)])
+    assert E.shape == (N, 6) and np.all(np.isfinite(E))
+    assert np.abs(E / ref - 1).max() < 1e-11
+    # scalar entry point
+    assert np.array_equal(sf.Eij_orthotropic(q1[5], q2[5], q3r[5], e1[5], e2[5], e3[5], OLIVINE, 0.0, 1), E[5])
+
+
+def test_Eij_orthotropic_pins_and_errors():
+    import specfab_b200 as sf
+    lm, n = sf.init(L)
+    x = np.zeros((9, n), dtype=np.complex128)
+    x[:, 0] = 1 / np.sqrt(4 * np.pi)
+    e1, e2, e3 = _frames(9, 2)
+    E = sf.Eij_orthotropic_arr(x, x, x, e1, e2, e3, OLIVINE, 0.0, 1)
+    assert np.abs(E - 1).max() < 1e-13
+    # isotropic grains (all Eij_grain = 1) never enhance, whatever the fabric
+    q1 = random_states(L, 9, 5, True, decay=0.35); q2 = random_states(L, 9, 6, True, decay=0.35)
+    E = sf.Eij_orthotropic_arr(q1, q2, 0 * q1, e1, e2, e3, (1, 1, 1, 1, 1, 1), 0.0, 1)
+    orc.init(L)
+    ref = np.array([orc.Eij_orthotropic(q1[p], q2[p], 0 * q1[p], e1[p], e2[p], e3[p], (1, 1, 1, 1, 1, 1), 0.0, 1) for p in range(9)])
+    assert np.abs(E / ref - 1).max() < 1e-11
+    # n_grain /= 1: the reference's 0/0
+    assert np.all(np.isnan(sf.Eij_orthotropic_arr(x, x, x, e1, e2, e3, OLIVINE, 0.0, 3)))
+    with pytest.raises(ValueError):
+        sf.Eij_orthotropic_arr(x, x, x, e1, e2, e3, (1.0, 10.0), 0.0, 1)
+    assert sf.Eij_orthotropic_arr(x[:0], x[:0], x[:0], e1[:0], e2[:0], e3[:0], OLIVINE, 0.0, 1).shape == (0, 6)
+
+
+def test_Eij_orthotropic_device_arrays():
+    import torch
+    import specfab_b200 as sf
+    sf.init(L)
+    N = 1000
+    q1 = random_states(L, N, 41, True, decay=0.35); q2 = random_states(L, N, 42, True, decay=0.35)
+    e1, e2, e3 = _frames(N, 43)
+    host = sf.Eij_orthotropic_arr(q1, q2, None, e1, e2, e3, OLIVINE, 0.0, 1)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    out = sf.Eij_orthotropic_arr_dev(dev(q1), dev(q2), None, dev(e1), dev(e2), dev(e3), OLIVINE, 0.0, 1)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().T, host)

@@ -4,6 +4,7 @@ restatement must reproduce them to rounding."""
 import os
 
 import numpy as np
+import pytest
 
 import specfab_oracle as o
 
@@ -129,3 +130,34 @@ def test_apply_bounds():
     x[3] = 5.0
     y = o.apply_bounds(x)
     assert abs(o.Sl(y, 2) / x[0].real ** 2 - 1) < 1e-14 and np.array_equal(y[6:], x[6:])
+
+
+@pytest.mark.parametrize("tag,fn", [("v2", "a2_orth"), ("v4", "a4_orth"), ("c2b2", "a4_joint"), ("c2v2", "a4_jointcross")])
+def test_orthotropic_moment_bodies(tag, fn):
+    """src/moments.f90:242-311: the coefficient tensors extracted symbolically from the generated include bodies
+    (tools/make_orthotropic_tables.py) against the numeric interpretation of the same text (tools/make_golden.py)"""
+    for c in range(G["orth_b"].shape[0]):
+        r = getattr(o, fn)(G["orth_b"][c], G["orth_n"][c])
+        ref = G["orth_" + tag][c]
+        assert r.shape == ref.shape
+        assert np.abs(r - ref).max() < 5e-15 * np.abs(ref).max()
+
+
+def test_orthotropic_enhancements_pins():
+    """isotropic b, n, v distributions -> Eij = 1; index symmetrisers of src/tensorproducts.f90:53-82"""
+    o.init(4)
+    o._check_sym4()
+    iso = np.zeros(15, complex); iso[0] = 1 / np.sqrt(4 * np.pi)
+    e = np.eye(3)
+    E = o.Eij_orthotropic(iso, iso, iso, e[0], e[1], e[2], (1, 1, 1, 1, 10, 1), 0.0, 1)
+    assert np.abs(E - 1).max() < 1e-14
+    # trace identities of the joint moments: <b^2 n^2 sin^2> contracts to 1, <v^2> has unit trace
+    rng = np.random.default_rng(3)
+    b = iso.copy(); n = iso.copy()
+    b[1:6] = 0.02 * (rng.standard_normal(5)); n[1:6] = 0.02 * rng.standard_normal(5)
+    for q in (b, n):        # impose n_l^-m = (-1)^m conj(n_l^m)
+        q[1], q[2] = q[5].conjugate(), -q[4].conjugate(); q[3] = q[3].real
+    assert abs(np.trace(o.a2_orth(b, n)) - 1) < 1e-6
+    assert abs(np.einsum("iijj", o.a4_joint(b, n)) - 1) < 1e-6
+    # n_grain /= 1 is "silently 0" in the reference's forward rheology -> 0/0
+    assert np.all(np.isnan(o.Eij_orthotropic(iso, iso, iso, e[0], e[1], e[2], (1, 1, 1, 1, 10, 1), 0.0, 3)))

@@ -151,6 +151,25 @@ for c in range(NCASE):
     gd_k[c] = env["k"].v
 out.update(sym=mats, skew=omgs, quad_rr=q2, quad_tp=q1, lrot_g=gw, ddrx_g=gd, ddrx_k=gd_k)
 
+# ---- orthotropic moment bodies (bilinear in two distributions, real(4) constants): numeric interpretation ----
+orth = {}
+NO = 3
+bq = rng.standard_normal((NO, 15)) + 1j * rng.standard_normal((NO, 15))
+nq = rng.standard_normal((NO, 15)) + 1j * rng.standard_normal((NO, 15))
+bq[:, 0] = 0.28 + 0.02 * rng.standard_normal(NO); nq[:, 0] = 0.28 + 0.02 * rng.standard_normal(NO)
+orth["orth_b"], orth["orth_n"] = bq, nq
+for tag, fn, rank in (("v2", "ev_v2__body.f90", 2), ("v4", "ev_v4__body.f90", 4), ("c2b2", "ev_c2b2__body.f90", 4), ("c2v2", "ev_c2v2__body.f90", 4)):
+    res = np.zeros((NO,) + (3,) * rank)
+    txt = rd("include", fn)
+    for c in range(NO):
+        env = {"Pi": PI, "b00": V("c8", bq[c, 0]), "b2m": cvec(bq[c, 1:6], -2), "b4m": cvec(bq[c, 6:15], -4),
+               "n00": V("c8", nq[c, 0]), "n2m": cvec(nq[c, 1:6], -2), "n4m": cvec(nq[c, 6:15], -4)}
+        run_body(txt, env, {"k": "r8", "ev": "r8", "norm": "r8"})
+        for key, val in env["ev"].items():
+            res[(c,) + tuple(i - 1 for i in key)] = val.v * env["k"].v / env["norm"].v      # ev = ev * k/norm  (src/moments.f90:257)
+    orth["orth_" + tag] = res
+out.update(orth)
+
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "refbodies.npz")
 np.savez_compressed(dst, **out)
 print("wrote", os.path.normpath(dst), {k: v.shape for k, v in out.items()})
