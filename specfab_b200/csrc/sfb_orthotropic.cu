@@ -7,12 +7,13 @@
 //     ev(e) = REAL( sum_t C_t b_{p_t} n_{q_t} ) * k / norm         (81 entries, 2.4k-5.6k terms each)
 // Every C_t is purely real or purely imaginary, so with P = (Re, Im) of the 15 x 15 products b_p n_q of one node,
 // ev(e) = sum_t coef_t * P[idx_t].  Work decomposition here: one CTA owns TN nodes; thread <-> tensor entry e
-// (81 of 96 lanes, rows sorted by length so the three warps are balanced); P of the TN nodes lives in shared memory,
+// (81 of 96 lanes, one entry order for all tables, sorted by row length so the three warps are balanced); P of the TN nodes lives in shared memory,
 // the ELL table streams through L1/L2 once per CTA (term-major, coalesced) and each term feeds TN DFMAs.
 // Everything downstream of the moment tensors is linear in them, so each lane only keeps three running
 // combinations per node (the a4_ii part, the sym2 part and the sym4 part of Q) for numerator and isotropic
 // denominator, weights them with vw (x) tau of the six (v,w) pairs and the CTA reduces over entries at the end.
 #include <cmath>
+#include <cstdlib>
 
 #include "sfb_fields.cuh"
 #include "gen/orth_tables.inc"
@@ -20,7 +21,6 @@
 namespace {
 
 constexpr int kLanes = SFB_ORTH_LANES;
-constexpr int kPS = 452;                 // P row stride (450 + pad)
 
 struct OrthCoef {                        // host-computed, src/rheologies.f90:186-206 + homogenizations.f90:303-304
     double cA[3];                        // weight of a4_ii(j) in Q: sum of ci(i)/4 over the M2(i) that contain it
@@ -41,7 +41,7 @@ __device__ __forceinline__ TabRef tab_c2v2() { return {kOrthCoef_2, kOrthIdx_2, 
 template <int TN>
 struct Smem {
     double2 q[3][TN][15];
-    double P[TN][kPS];
+    double P[450][TN];          // (Re, Im) of b_p n_q, node-minor: one term reads the TN nodes with vector loads
     double U[TN][4][15];        // unique a4 entries of q1, q2, q3 and of the isotropic state
     double F[TN][6][18];        // per Eij component: vw(3,3) then tau(3,3), row-major
     double red[3][TN * 12];
@@ -53,10 +53,10 @@ struct Smem {
 template <int TN>
 __device__ __forceinline__ void make_P(Smem<TN>& s, int ib, int in) {
     for (int w = threadIdx.x; w < TN * 225; w += kLanes) {
-        const int i = w / 225, pq = w - i * 225, p = pq / 15, q = pq - p * 15;
+        const int pq = w / TN, i = w - pq * TN, p = pq / 15, q = pq - p * 15;
         const double2 b = s.q[ib][i][p], n = s.q[in][i][q];
-        s.P[i][2 * pq] = b.x * n.x - b.y * n.y;
-        s.P[i][2 * pq + 1] = b.x * n.y + b.y * n.x;
+        s.P[2 * pq][i] = b.x * n.x - b.y * n.y;
+        s.P[2 * pq + 1][i] = b.x * n.y + b.y * n.x;
     }
 }
 
@@ -69,34 +69,38 @@ __device__ __forceinline__ void eval_table(const TabRef& T, const Smem<TN>& s, i
     for (int i = 0; i < TN; ++i) acc[i] = 0.0;
     const double* cp = T.coef + lane;
     const unsigned short* ip = T.idx + lane;
-#pragma unroll 2
+#pragma unroll 4
     for (int t = 0; t < len; ++t) {
         const double c = cp[t * kLanes];
-        const int ix = ip[t * kLanes];
+        const double2* pr = reinterpret_cast<const double2*>(s.P[ip[t * kLanes]]);
 #pragma unroll
-        for (int i = 0; i < TN; ++i) acc[i] = fma(c, s.P[i][ix], acc[i]);
+        for (int i = 0; i < TN / 2; ++i) {
+            const double2 v = pr[i];
+            acc[2 * i] = fma(c, v.x, acc[2 * i]);
+            acc[2 * i + 1] = fma(c, v.y, acc[2 * i + 1]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < TN; ++i) {
         double nrm = 0.0;
-        for (int t = 0; t < T.nnorm; ++t) nrm += T.ncoef[t] * s.P[i][T.nidx[t]];
+        for (int t = 0; t < T.nnorm; ++t) nrm += T.ncoef[t] * s.P[T.nidx[t]][i];
         ev[i] = acc[i] * T.k / nrm;
     }
 }
 
 // the same table evaluated on the isotropic pair (only the b00 n00 term survives), z = qlm_1(1)^2
 __device__ __forceinline__ double eval_iso(const TabRef& T, int e, double zr, double zi) {
-    const double pz[2] = {zr, zi};
-    return T.iso_coef[e] * pz[T.iso_im[e]] * T.k / (T.ncoef[0] * zr);
+    return T.iso_coef[e] * (T.iso_im[e] ? zi : zr) * T.k / (T.ncoef[0] * zr);
 }
 
 template <int TN>
-__global__ void __launch_bounds__(kLanes) eij_orth_kernel(const double2* __restrict__ q1, long long ld1,
-                                                          const double2* __restrict__ q2, long long ld2,
-                                                          const double2* __restrict__ q3, long long ld3, long long N,
-                                                          const double* __restrict__ e1, const double* __restrict__ e2,
-                                                          const double* __restrict__ e3, long long lde, OrthCoef K,
-                                                          double* __restrict__ Eij, long long ldo) {
+__global__ void __launch_bounds__(kLanes, 4) eij_orth_kernel(const double2* __restrict__ q1, long long ld1,
+                                                             const double2* __restrict__ q2, long long ld2,
+                                                             const double2* __restrict__ q3, long long ld3, long long N,
+                                                             const double* __restrict__ e1, const double* __restrict__ e2,
+                                                             const double* __restrict__ e3, long long lde, OrthCoef K,
+                                                             double* __restrict__ Eij, long long ldo) {
+    static_assert(TN % 2 == 0, "node tile must be even");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<TN>& s = *reinterpret_cast<Smem<TN>*>(smem_raw);
     const int lane = threadIdx.x;
@@ -105,13 +109,11 @@ __global__ void __launch_bounds__(kLanes) eij_orth_kernel(const double2* __restr
     // ---- stage the three states (rows 0..14) and the frames
     for (int w = lane; w < 3 * TN * 15; w += kLanes) {
         const int a = w / (TN * 15), r = (w / TN) % 15, i = w % TN;
-        const long long p = p0 + i;
-        double2 v = make_double2(r == 0 ? 1.0 : 0.0, 0.0);
-        if (p < N) {
-            if (a == 0) v = q1[(long long)r * ld1 + p];
-            else if (a == 1) v = q2[(long long)r * ld2 + p];
-            else v = q3 ? q3[(long long)r * ld3 + p] : make_double2(0.0, 0.0);
-        }
+        const long long p = min(p0 + i, N - 1);             // tail nodes replicate the last one (never stored)
+        double2 v = make_double2(0.0, 0.0);
+        if (a == 0) v = q1[(long long)r * ld1 + p];
+        else if (a == 1) v = q2[(long long)r * ld2 + p];
+        else if (q3) v = q3[(long long)r * ld3 + p];
         s.q[a][i][r] = v;
     }
     if (lane < TN * 6) {
@@ -152,157 +154,114 @@ __global__ void __launch_bounds__(kLanes) eij_orth_kernel(const double2* __restr
     make_P(s, 0, 1);
     __syncthreads();
 
-    int any3 = 0, anyno3 = 0;
+    int any3 = 0, anyno3 = 0, anyiso_no3 = 0;
 #pragma unroll
-    for (int i = 0; i < TN; ++i) { any3 |= s.has3[i]; anyno3 |= !s.has3[i]; }
+    for (int i = 0; i < TN; ++i) { any3 |= s.has3[i]; anyno3 |= !s.has3[i]; anyiso_no3 |= !s.iso3[i]; }
 
-    // entry handled by this lane under the c2b2 lane order (all three tables share one order? no: per table)
-    double SA[TN], S2[TN], S4[TN];        // numerator combinations of THIS lane's entry, per table order
-    double accN[TN][6], accD[TN][6];
-#pragma unroll
-    for (int i = 0; i < TN; ++i)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { accN[i][c] = 0.0; accD[i][c] = 0.0; }
+    // the three tables share one lane <-> entry map, so the lane accumulates, for its entry e and each node, the
+    // a4_ii combination (A), the weight of a4_sym2 (S2) and of a4_sym4 (S4); D* are the same for the isotropic state
+    const TabRef Tb = tab_c2b2(), Tv = tab_v4(), Tc = tab_c2v2();
+    const int e = Tb.perm[lane];
+    const bool live = e < 81;
+    const int x0 = e % 3, x1 = (e / 3) % 3, x2 = (e / 9) % 3, x3 = e / 27;
+    // src/include/ev_c4__body.f90:78: ev(3,2,1,2) aliases ev(1,2,3,3)
+    const int uq = !live ? 0 : ((x0 == 2 && x1 == 1 && x2 == 0 && x3 == 1) ? 8 : sfb::a4_unique_index(x0, x1, x2, x3));
+    double A[TN], S2[TN], S4[TN], DA[TN], D2[TN], D4[TN], ev[TN];
 
-    // weight the running combinations of entry e and add to the per-component sums
-    auto flush = [&](int e, const double* sa, const double* s2, const double* s4, double (*acc)[6]) {
-        if (e >= 81) return;
-        const int x0 = e % 3, x1 = (e / 3) % 3, x2 = (e / 9) % 3, x3 = e / 27;
+    // ---- c2b2(q1,q2) = a4_jk(3); a4_ii(1), a4_ii(2) (+ a4_ii(3) when qlm_3 is given)
+    eval_table<TN>(Tb, s, lane, ev);
 #pragma unroll
-        for (int i = 0; i < TN; ++i)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const double* vw = s.F[i][c];
-                const double* tau = vw + 9;
-                // E = Q_lkij vw_kl tau_ji   (doubleinner42 then doubleinner22; src/tensorproducts.f90:153-179)
-                auto W = [&](int l, int k, int ii, int jj) { return vw[3 * k + l] * tau[3 * jj + ii]; };
-                const double wA = W(x0, x1, x2, x3);
-                const double w2 = 0.5 * (wA + W(x2, x3, x0, x1));                                   // a4_sym2  :53-64
-                const double w4 = 0.25 * (W(x0, x2, x1, x3) + W(x2, x1, x0, x3) + W(x0, x3, x2, x1) + W(x3, x1, x2, x0));  // a4_sym4 :66-82
-                acc[i][c] += wA * sa[i] + w2 * s2[i] + w4 * s4[i];
-            }
-    };
-    auto u_index = [](int e) {
-        const int a = e % 3, b = (e / 3) % 3, c = (e / 9) % 3, d = e / 27;
-        return (a == 2 && b == 1 && c == 0 && d == 1) ? 8 : sfb::a4_unique_index(a, b, c, d);   // src/include/ev_c4__body.f90:78
-    };
-
-    double ev[TN];
-    // ---- pass 1: c2b2(q1,q2) = a4_jk(3); the a4_ii(1), a4_ii(2) (+ a4_ii(3) when qlm_3 is given) terms ride along
-    {
-        const TabRef T = tab_c2b2();
-        const int e = T.perm[lane];
-        eval_table<TN>(T, s, lane, ev);
-        const int uq = e < 81 ? u_index(e) : 0;
-#pragma unroll
-        for (int i = 0; i < TN; ++i) {
-            SA[i] = K.cA[0] * s.U[i][0][uq] + K.cA[1] * s.U[i][1][uq] + (s.has3[i] ? K.cA[2] * s.U[i][2][uq] : 0.0);
-            S2[i] = K.cJ2[2] * ev[i];
-            S4[i] = K.cJ4[2] * ev[i];
+    for (int i = 0; i < TN; ++i) {
+        A[i] = K.cA[0] * s.U[i][0][uq] + K.cA[1] * s.U[i][1][uq] + (s.has3[i] ? K.cA[2] * s.U[i][2][uq] : 0.0);
+        S2[i] = K.cJ2[2] * ev[i];
+        S4[i] = K.cJ4[2] * ev[i];
+        // isotropic stand-in: every tensor of the "given" branch collapses to a4(iso) / c2b2(iso,iso)
+        const double2 b0 = s.q[0][i][0];
+        const double zr = b0.x * b0.x - b0.y * b0.y, zi = 2.0 * b0.x * b0.y;
+        const double ui = s.U[i][3][uq];
+        const double jb = live ? eval_iso(Tb, e, zr, zi) : 0.0;
+        if (s.iso3[i]) {
+            DA[i] = (K.cA[0] + K.cA[1] + K.cA[2]) * ui;
+            D2[i] = (K.cJ2[0] + K.cJ2[1] + K.cJ2[2]) * jb;
+            D4[i] = (K.cJ4[0] + K.cJ4[1] + K.cJ4[2]) * jb;
+        } else {   // degenerate qlm_1(1) <= 1e-8: the derived-axis closures of the isotropic pair
+            const double jc = live ? eval_iso(Tc, e, zr, zi) : 0.0;
+            DA[i] = (K.cA[0] + K.cA[1]) * ui + (live ? K.cA[2] * eval_iso(Tv, e, zr, zi) : 0.0);
+            D2[i] = K.cJ2[2] * jb + (K.cJ2[0] + K.cJ2[1]) * jc;
+            D4[i] = K.cJ4[2] * jb + (K.cJ4[0] + K.cJ4[1]) * jc;
         }
-        if (any3) {          // a4_jk(1) = c2b2(q2,q3), a4_jk(2) = c2b2(q1,q3)
-            for (int pass = 0; pass < 2; ++pass) {
-                __syncthreads();
-                make_P(s, pass == 0 ? 1 : 0, 2);
-                __syncthreads();
-                eval_table<TN>(T, s, lane, ev);
-#pragma unroll
-                for (int i = 0; i < TN; ++i)
-                    if (s.has3[i]) { S2[i] += K.cJ2[pass] * ev[i]; S4[i] += K.cJ4[pass] * ev[i]; }
-            }
-        }
-        flush(e, SA, S2, S4, accN);
-        // isotropic denominator, qlm_3 "given" branch
-        const double2 z0 = s.q[0][0][0];
-        (void)z0;
-#pragma unroll
-        for (int i = 0; i < TN; ++i) {
-            const double2 b0 = s.q[0][i][0];
-            const double zr = b0.x * b0.x - b0.y * b0.y, zi = 2.0 * b0.x * b0.y;
-            const double j = e < 81 ? eval_iso(T, e, zr, zi) : 0.0;
-            const double ui = s.U[i][3][uq];
-            if (s.iso3[i]) {
-                SA[i] = (K.cA[0] + K.cA[1] + K.cA[2]) * ui;          // summed in the same order as Q below is irrelevant at 1e-12
-                S2[i] = (K.cJ2[0] + K.cJ2[1] + K.cJ2[2]) * j;
-                S4[i] = (K.cJ4[0] + K.cJ4[1] + K.cJ4[2]) * j;
-            } else {
-                SA[i] = (K.cA[0] + K.cA[1]) * ui;
-                S2[i] = K.cJ2[2] * j;
-                S4[i] = K.cJ4[2] * j;
-            }
-        }
-        flush(e, SA, S2, S4, accD);
     }
-    // ---- derived third axis: a4_ii(3) = a4_orth(q1,q2), a4_jk(1) = jointcross(q2,q1), a4_jk(2) = jointcross(q1,q2)
-    int anyiso_no3 = 0;
-#pragma unroll
-    for (int i = 0; i < TN; ++i) anyiso_no3 |= !s.iso3[i];
-    if (anyno3 || anyiso_no3) {
-        __syncthreads();
-        make_P(s, 0, 1);
-        __syncthreads();
-        {
-            const TabRef T = tab_v4();
-            const int e = T.perm[lane];
-            eval_table<TN>(T, s, lane, ev);
-#pragma unroll
-            for (int i = 0; i < TN; ++i) { SA[i] = s.has3[i] ? 0.0 : K.cA[2] * ev[i]; S2[i] = 0.0; S4[i] = 0.0; }
-            flush(e, SA, S2, S4, accN);
-#pragma unroll
-            for (int i = 0; i < TN; ++i) {
-                const double2 b0 = s.q[0][i][0];
-                const double zr = b0.x * b0.x - b0.y * b0.y, zi = 2.0 * b0.x * b0.y;
-                SA[i] = (s.iso3[i] || e >= 81) ? 0.0 : K.cA[2] * eval_iso(T, e, zr, zi);
-            }
-            flush(e, SA, S2, S4, accD);
-        }
-        {
-            const TabRef T = tab_c2v2();
-            const int e = T.perm[lane];
-            eval_table<TN>(T, s, lane, ev);                   // jointcross(q1,q2) = a4_jk(2)
-#pragma unroll
-            for (int i = 0; i < TN; ++i) { SA[i] = 0.0; S2[i] = s.has3[i] ? 0.0 : K.cJ2[1] * ev[i]; S4[i] = s.has3[i] ? 0.0 : K.cJ4[1] * ev[i]; }
+    if (any3) {          // a4_jk(1) = c2b2(q2,q3), a4_jk(2) = c2b2(q1,q3)
+        for (int pass = 0; pass < 2; ++pass) {
             __syncthreads();
-            make_P(s, 1, 0);
+            make_P(s, pass == 0 ? 1 : 0, 2);
             __syncthreads();
-            eval_table<TN>(T, s, lane, ev);                   // jointcross(q2,q1) = a4_jk(1)
+            eval_table<TN>(Tb, s, lane, ev);
 #pragma unroll
             for (int i = 0; i < TN; ++i)
-                if (!s.has3[i]) { S2[i] += K.cJ2[0] * ev[i]; S4[i] += K.cJ4[0] * ev[i]; }
-            flush(e, SA, S2, S4, accN);
-#pragma unroll
-            for (int i = 0; i < TN; ++i) {
-                const double2 b0 = s.q[0][i][0];
-                const double zr = b0.x * b0.x - b0.y * b0.y, zi = 2.0 * b0.x * b0.y;
-                const double j = (s.iso3[i] || e >= 81) ? 0.0 : eval_iso(T, e, zr, zi);
-                S2[i] = (K.cJ2[0] + K.cJ2[1]) * j;
-                S4[i] = (K.cJ4[0] + K.cJ4[1]) * j;
-            }
-            flush(e, SA, S2, S4, accD);
+                if (s.has3[i]) { S2[i] += K.cJ2[pass] * ev[i]; S4[i] += K.cJ4[pass] * ev[i]; }
         }
     }
-
-    // ---- reduce over the 81 entries: warp shuffle, then across the three warps through shared memory
-    const int warp = lane >> 5;
-#pragma unroll
-    for (int i = 0; i < TN; ++i)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            double a = accN[i][c], b = accD[i][c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            if ((lane & 31) == 0) { s.red[warp][i * 12 + c] = a; s.red[warp][i * 12 + 6 + c] = b; }
+    // ---- derived third axis: a4_ii(3) = a4_orth(q1,q2), a4_jk(2) = jointcross(q1,q2), a4_jk(1) = jointcross(q2,q1)
+    if (anyno3) {
+        if (any3) {
+            __syncthreads();
+            make_P(s, 0, 1);
+            __syncthreads();
         }
+        eval_table<TN>(Tv, s, lane, ev);
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+            if (!s.has3[i]) A[i] += K.cA[2] * ev[i];
+        eval_table<TN>(Tc, s, lane, ev);
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+            if (!s.has3[i]) { S2[i] += K.cJ2[1] * ev[i]; S4[i] += K.cJ4[1] * ev[i]; }
+        __syncthreads();
+        make_P(s, 1, 0);
+        __syncthreads();
+        eval_table<TN>(Tc, s, lane, ev);
+#pragma unroll
+        for (int i = 0; i < TN; ++i)
+            if (!s.has3[i]) { S2[i] += K.cJ2[0] * ev[i]; S4[i] += K.cJ4[0] * ev[i]; }
+    }
+    (void)anyiso_no3;
+
+    // ---- E = Q_lkij vw_kl tau_ji  (doubleinner42 then doubleinner22; src/tensorproducts.f90:153-179):
+    // weight the lane's entry for each node and component, reduce over the 81 entries
+    const int warp = lane >> 5;
+#pragma unroll 1
+    for (int ic = 0; ic < TN * 6; ++ic) {
+        const int i = ic / 6;
+        const double* vw = s.F[0][0] + ic * 18;
+        const double* tau = vw + 9;
+        auto W = [&](int l, int k, int ii, int jj) { return vw[3 * k + l] * tau[3 * jj + ii]; };
+        double num = 0.0, den = 0.0;
+        if (live) {
+            const double wA = W(x0, x1, x2, x3);
+            const double w2 = 0.5 * (wA + W(x2, x3, x0, x1));                                                            // a4_sym2 :53-64
+            const double w4 = 0.25 * (W(x0, x2, x1, x3) + W(x2, x1, x0, x3) + W(x0, x3, x2, x1) + W(x3, x1, x2, x0));    // a4_sym4 :66-82
+            double a = 0, b2 = 0, b4 = 0, da = 0, d2 = 0, d4 = 0;
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+                if (j == i) { a = A[j]; b2 = S2[j]; b4 = S4[j]; da = DA[j]; d2 = D2[j]; d4 = D4[j]; }
+            num = wA * a + w2 * b2 + w4 * b4;
+            den = wA * da + w2 * d2 + w4 * d4;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            num += __shfl_xor_sync(0xffffffffu, num, o);
+            den += __shfl_xor_sync(0xffffffffu, den, o);
+        }
+        if ((lane & 31) == 0) { s.red[warp][2 * ic] = num; s.red[warp][2 * ic + 1] = den; }
+    }
     __syncthreads();
     if (lane < TN * 6) {
         const int i = lane / 6, c = lane % 6;
         const long long p = p0 + i;
         if (p < N) {
-            const double num = s.red[0][i * 12 + c] + s.red[1][i * 12 + c] + s.red[2][i * 12 + c];
-            const double den = s.red[0][i * 12 + 6 + c] + s.red[1][i * 12 + 6 + c] + s.red[2][i * 12 + 6 + c];
+            const double num = s.red[0][2 * lane] + s.red[1][2 * lane] + s.red[2][2 * lane];
+            const double den = s.red[0][2 * lane + 1] + s.red[1][2 * lane + 1] + s.red[2][2 * lane + 1];
             // n_grain /= 1: the reference's forward rheology silently returns 0, so Evw = 0/0   (homogenizations.f90:316-318)
             Eij[(long long)c * ldo + p] = K.linear ? num / den : nan("");
         }
@@ -327,15 +286,17 @@ cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2*
     K.cA[0] = (ci[1] + ci[2]) / 4; K.cA[1] = (ci[0] + ci[2]) / 4; K.cA[2] = (ci[0] + ci[1]) / 4;
     for (int i = 0; i < 3; ++i) { K.cJ2[i] = -ci[i] / 2; K.cJ4[i] = ci[3 + i]; }
     K.linear = n_grain == 1;
-    constexpr int TN = 4;
-    static bool attr_done = false;
-    const size_t smem = sizeof(Smem<TN>);
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(eij_orth_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
+    // node tile per CTA: 4 by default; SFB_ORTH_TN=8 selects the larger tile (tuning knob, profiles/r01_notes.md)
+    static int tn = 0;
+    if (!tn) {
+        const char* ev = getenv("SFB_ORTH_TN");
+        tn = (ev && atoi(ev) == 8) ? 8 : 4;
+        cudaError_t e = cudaFuncSetAttribute(eij_orth_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<4>));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(eij_orth_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<8>));
+        if (e != cudaSuccess) { tn = 0; return e; }
     }
-    const unsigned blocks = (unsigned)((N + TN - 1) / TN);
-    eij_orth_kernel<TN><<<blocks, kLanes, smem, st>>>(q1, ld1, q2, ld2, q3, ld3, N, e1, e2, e3, lde, K, Eij, ldo);
+    const unsigned blocks = (unsigned)((N + tn - 1) / tn);
+    if (tn == 8) eij_orth_kernel<8><<<blocks, kLanes, sizeof(Smem<8>), st>>>(q1, ld1, q2, ld2, q3, ld3, N, e1, e2, e3, lde, K, Eij, ldo);
+    else eij_orth_kernel<4><<<blocks, kLanes, sizeof(Smem<4>), st>>>(q1, ld1, q2, ld2, q3, ld3, N, e1, e2, e3, lde, K, Eij, ldo);
     return cudaGetLastError();
 }
