@@ -97,8 +97,9 @@ int sfb_eigframe_arr(const double* M, int64_t N, const char* plane, double* ei, 
 int sfb_eigframe_arr_dev(const double* M, int64_t N, int64_t ld, const char* plane, double* ei, double* lami, void* stream);
 /* Eij_tranisotropic_arr(nlm, e1,e2,e3 (N,3), Eij_grain(2), alpha, n_grain) -> Eij(N,6) = (E11,E22,E33,E23,E13,E12)
  *                                            src/specfabpy.f90:474-486, src/enhancementfactors.f90:23-69.
- * Only n_grain = 1.  status (optional, [N]) receives SFB_ST_* flags instead of the reference's `stop`
- * (src/homogenizations.f90:183). */
+ * n_grain = 1, 3 (Sachs through a6/a8, needs L >= 8; src/homogenizations.f90:93-102) or -3 (:105-109); the Taylor
+ * part is the n'=1 solve in every case like the reference (:148).  status (optional, [N]) receives SFB_ST_* flags
+ * instead of the reference's `stop` (src/homogenizations.f90:183). */
 int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
                               const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status);
 int sfb_Eij_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
@@ -110,6 +111,18 @@ int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const doubl
 int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
                                double* Eij, double* ei, double* lami, int32_t* status, void* stream);
 
+/* a6 of every node -> (N,3,3,3,3,3,3) Fortran order (needs L >= 6)          src/specfabpy.f90:601-608, src/moments.f90:57-66 */
+int sfb_a6_arr(const double* nlm, int64_t N, int64_t ld, double* a6);
+int sfb_a6_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a6, void* stream);
+/* E_CAFFE_arr(nlm, eps (N,3,3), Emin, Emax, n_grain) -> E(N)                 src/specfabpy.f90:543-554,
+ * src/enhancementfactors.f90:301-331.  n_grain = 3 uses <D> from RSS^4 (ev_D4, needs L >= 8), anything else RSS^2. */
+int sfb_E_CAFFE_arr(const double* nlm, int64_t N, int64_t ld, const double* eps, double Emin, double Emax, int n_grain, double* E);
+int sfb_E_CAFFE_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* eps, double Emin, double Emax, int n_grain, double* E,
+                        void* stream);
+/* pfJ(nlm, Lmax) of every node -> J(N): pole-figure J index truncated at Lmax <= L     src/specfabpy.f90:729-736,
+ * src/idealstate.f90:111-124 */
+int sfb_pfJ_arr(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J);
+int sfb_pfJ_arr_dev(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J, void* stream);
 /* Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3 (N,nlm_len), e1,e2,e3 (N,3), Eij_grain(6), alpha, n_grain) -> Eij(N,6)
  *                                            src/specfabpy.f90:488-500, src/enhancementfactors.f90:134-189.
  * Orthotropic grains (olivine): nlm_1..3 are the distributions of the slip-system axes (b, n, v); where

@@ -447,6 +447,131 @@ def a4(nlm):
 
 
 # ---------------------------------------------------------------------------------------------
+# 6th / 8th order structure tensors (src/moments.f90:57-66,137-162,220-236)
+# ---------------------------------------------------------------------------------------------
+# ev_c6__body.f90 / ev_c8__body.f90 are 0.26 / 3.9 MB of generated linear forms with real(4) constants; like the
+# orthotropic bodies they are not transcribed: tools/make_moment_tables.py interprets the reference text once and
+# stores the coefficients of the canonical (sorted-index) entries -- the reference's 3^k separate assignments are
+# exactly permutation symmetric (measured deviation 0, stored as *_permdev).  tests/golden pins them.
+
+_HI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "specfab_b200", "data", "moments_l8.npz")
+_hi_cache = {}
+
+
+def _hi_tables():
+    if not _hi_cache:
+        import itertools
+        d = np.load(_HI)
+        for tag, rank in (("c6", 6), ("c8", 8)):
+            uniq = {t: u for u, t in enumerate(itertools.combinations_with_replacement((0, 1, 2), rank))}
+            full = np.zeros((3,) * rank, dtype=np.int64)
+            for idx in itertools.product((0, 1, 2), repeat=rank):
+                full[idx] = uniq[tuple(sorted(idx))]
+            M = np.zeros((len(uniq), 45), dtype=np.complex128)
+            M[d[tag + "_u"], d[tag + "_j"]] = d[tag + "_c"]
+            _hi_cache[tag] = (M, float(d[tag + "_k"]), full)
+    return _hi_cache
+
+
+def _f_ev_hi(tag, nlm):
+    M, k, full = _hi_tables()[tag]
+    x = np.zeros(45, dtype=np.complex128)
+    v = np.asarray(nlm, dtype=np.complex128)[:45]
+    x[:v.size] = v
+    u = (M @ x).real * k / f_ev_c0(complex(x[0]))          # ev = ev * k/f_ev_c0(n00)   src/moments.f90:226,235
+    return u[full]
+
+
+def a6(nlm):
+    """src/moments.f90:57-66 + f_ev_c6 (:220-227)"""
+    return _f_ev_hi("c6", nlm)
+
+
+def a8(nlm):
+    """f_ev_c8, src/moments.f90:229-236"""
+    return _f_ev_hi("c8", nlm)
+
+
+def f_ev_ck(nlm, opt="f"):
+    """src/moments.f90:137-162 -> (ev_c2, ev_c4, ev_c6, ev_c8)"""
+    n00, n2m, n4m = decompose_nlm(nlm)
+    c2, c4 = f_ev_c2(n00, n2m), f_ev_c4(n00, n2m, n4m)
+    if opt == "f":
+        return c2, c4, a6(nlm), a8(nlm)
+    return c2, c4, np.zeros((3,) * 6), np.zeros((3,) * 8)
+
+
+def doubleinner42(A, B):
+    """src/tensorproducts.f90:169-179: A_lkij B_ji"""
+    return np.einsum("lkij,ji->lk", A, B)
+
+
+def doubleinner44(A, B):
+    """src/tensorproducts.f90:205-211: A_lkij B_jikl"""
+    return float(np.einsum("lkij,jikl->", A, B))
+
+
+def doubleinner62(A, B):
+    """src/tensorproducts.f90:213-227: A_nmlkij B_ji"""
+    return np.einsum("nmlkij,ji->nmlk", A, B)
+
+
+def doubleinner82(A, B):
+    """src/tensorproducts.f90:229-247: A_ponmlkij B_ji"""
+    return np.einsum("ponmlkij,ji->ponmlk", A, B)
+
+
+def doubleinner84(A, B):
+    """src/tensorproducts.f90:249-263: A_ponmlkij B_jikl"""
+    return np.einsum("ponmlkij,jikl->ponm", A, B)
+
+
+def outerprodmat2(A, B):
+    """src/tensorproducts.f90:129-135: A_ij B_kl"""
+    return np.einsum("ij,kl->ijkl", A, B)
+
+
+def ev_D4(nlm, tau):
+    """src/dynamics.f90:424-448: average basal-plane RSS to the fourth power"""
+    tau = np.asarray(tau, dtype=np.float64)
+    tausq = tau @ tau
+    tautau = outerprodmat2(tau, tau)
+    tausqtau = outerprodmat2(tausq, tau)
+    norm = tausq[0, 0] + tausq[1, 1] + tausq[2, 2]
+    c2, c4, c6, c8 = f_ev_ck(nlm, "f")
+    D = doubleinner22(tausq, doubleinner42(c4, tausq))
+    D = D + doubleinner44(tautau, doubleinner84(c8, tautau))
+    D = D - 2 * doubleinner44(tausqtau, doubleinner62(c6, tau))
+    with np.errstate(all="ignore"):
+        return float(35 / 2.0 * np.float64(D) / np.float64(norm ** 2))
+
+
+def ev_D(nlm, tau, pw):
+    """src/dynamics.f90:380-400"""
+    return ev_D2(nlm, tau) if pw == 2 else (ev_D4(nlm, tau) if pw == 4 else 0.0)
+
+
+def E_CAFFE(nlm, eps, Emin, Emax, n_grain):
+    """src/enhancementfactors.f90:301-331 (Placidi et al. 2010)"""
+    Dmax = [0.0, 5 / 2.0, 0.0, 35 / 8.0]
+    n_RSS = 4 if n_grain == 3 else 2
+    D = ev_D(nlm, eps, n_RSS)
+    Dmaxpow = math.pow(Dmax[n_RSS - 1], 4.0 / n_RSS)
+    if D < 1:
+        gam = (4.0 / n_RSS) / Dmaxpow * (Emax - 1) / (1 - Emin)
+        with np.errstate(all="ignore"):
+            return float(Emin + (1 - Emin) * np.power(np.float64(D), gam))     # D < 0 -> NaN like Fortran's real**real
+    return ((Emax - 1) * math.pow(D, 4.0 / n_RSS) + Dmaxpow - Emax) / (Dmaxpow - 1)
+
+
+def pfJ(nlm, Lmax=None):
+    """src/idealstate.f90:111-124: pole-figure J index truncated at Lmax"""
+    L, _ = _L()
+    Lmax = L if Lmax is None else Lmax
+    return 4 * Pi * sum((2 * l + 1) * Sl(nlm, l) for l in range(0, Lmax + 1, 2))
+
+
+# ---------------------------------------------------------------------------------------------
 # frames.f90
 # ---------------------------------------------------------------------------------------------
 
@@ -492,17 +617,43 @@ def rheo_params_tranisotropic(Eij, d, n, ef):
     return cI, cM, cL
 
 
+def _sachs_eps(tau, I2, cA, cB, cC, ev_etac0, ev_etac2, a4tau):
+    """last line of src/homogenizations.f90:115 / :218"""
+    return ev_etac0 * tau - cA * doubleinner22(ev_etac2, tau) * np.eye(3) + cB * a4tau + cC * (tau @ ev_etac2 + ev_etac2 @ tau)
+
+
+def _sachs_n3_terms(tau, cB, cC, c2, c4, c6, c8):
+    """<eta c^k> terms of the n'=3 branch, src/homogenizations.f90:97-102 (also :212-216 with the isotropic tensors)"""
+    I2 = doubleinner22(tau, tau)
+    tausq = tau @ tau
+    ev_etac0 = I2 * 1.0 + cB * doubleinner22(doubleinner42(c4, tau), tau) + 2 * cC * doubleinner22(c2, tausq)
+    ev_etac2 = I2 * c2 + cB * doubleinner42(doubleinner62(c6, tau), tau) + 2 * cC * doubleinner42(c4, tausq)
+    ev_etac4 = I2 * c4 + cB * doubleinner62(doubleinner82(c8, tau), tau) + 2 * cC * doubleinner62(c6, tausq)
+    return ev_etac0, ev_etac2, doubleinner42(ev_etac4, tau)
+
+
 def rheo_fwd_tranisotropic_sachshomo(tau, nlm, Eij_grain, n_grain):
-    """src/homogenizations.f90:69-116 (n_grain == 1 branch)"""
-    if n_grain != 1:
-        raise NotImplementedError("oracle covers n'=1 only")
+    """src/homogenizations.f90:69-116 (n_grain = 1, 3 and -3)"""
     tau = np.asarray(tau, dtype=np.float64)
     cA, cB, cC = rheo_params_tranisotropic(Eij_grain, 3, float(n_grain), 1)
-    a2v, a4v = f_ev_ck_Mandel(nlm)
-    ev_etac0 = 1.0
-    ev_etac2 = vec_to_mat(a2v)
-    a4tau = vec_to_mat(a4v @ mat_to_vec(tau))
-    return ev_etac0 * tau - cA * doubleinner22(ev_etac2, tau) * np.eye(3) + cB * a4tau + cC * (tau @ ev_etac2 + ev_etac2 @ tau)
+    I2 = doubleinner22(tau, tau)
+    if n_grain == 1:
+        a2v, a4v = f_ev_ck_Mandel(nlm)
+        ev_etac0 = 1.0
+        ev_etac2 = vec_to_mat(a2v)
+        a4tau = vec_to_mat(a4v @ mat_to_vec(tau))
+    elif n_grain == 3:
+        if np.asarray(nlm).size < 45:
+            raise ValueError("specfab error: Sachs homogenization with n'=3 requires L >= 8.")
+        ev_etac0, ev_etac2, a4tau = _sachs_n3_terms(tau, cB, cC, *f_ev_ck(nlm, "f"))
+    elif n_grain == -3:
+        a2v, a4v = f_ev_ck_Mandel(nlm)
+        ev_etac0 = I2 * 1.0
+        ev_etac2 = I2 * vec_to_mat(a2v)
+        a4tau = I2 * vec_to_mat(a4v @ mat_to_vec(tau))
+    else:
+        raise ValueError("specfab error: unsupported n'")
+    return _sachs_eps(tau, I2, cA, cB, cC, ev_etac0, ev_etac2, a4tau)
 
 
 def anticommutator_Mandel(a):
@@ -548,10 +699,30 @@ def rheo_fwd_tranisotropic_taylorhomo(tau, nlm, Eij_grain, n_grain, return_statu
     return (eps, status) if return_status else eps
 
 
+_iso_ck = {}
+
+
+def _ev_ck_iso():
+    """src/homogenizations.f90:58-62: a^(k) of the isotropic state through the same f_ev_ck (real(4) round-off included)"""
+    if not _iso_ck:
+        x = np.zeros(45, dtype=np.complex128); x[0] = 1 / math.sqrt(4 * Pi)
+        _iso_ck["t"] = f_ev_ck(x, "f")
+    return _iso_ck["t"]
+
+
 def rheo_fwd_tranisotropic_sachshomo__isotropic(tau, Eij_grain, n_grain):
-    """src/homogenizations.f90:191-222 (n'=1)"""
+    """src/homogenizations.f90:191-222"""
+    tau = np.asarray(tau, dtype=np.float64)
     cA, cB, cC = rheo_params_tranisotropic(Eij_grain, 3, float(n_grain), 1)
-    return (1 + 2.0 / 15 * cB + 2.0 / 3 * cC) * np.asarray(tau, dtype=np.float64)
+    I2 = doubleinner22(tau, tau)
+    if n_grain == 1:
+        return (1 + 2.0 / 15 * cB + 2.0 / 3 * cC) * tau
+    if n_grain == -3:
+        return I2 * tau
+    if n_grain == 3:
+        ev_etac0, ev_etac2, a4tau = _sachs_n3_terms(tau, cB, cC, *_ev_ck_iso())
+        return _sachs_eps(tau, I2, cA, cB, cC, ev_etac0, ev_etac2, a4tau)
+    raise ValueError("specfab error: unsupported n'")
 
 
 def rheo_fwd_tranisotropic_taylorhomo__isotropic(tau, Eij_grain, n_grain):

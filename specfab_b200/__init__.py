@@ -21,7 +21,7 @@ from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, Sp
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
-           "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
+           "a6", "a6_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
 
 _state = {"L": None, "n": None}
@@ -267,12 +267,13 @@ def rnlm_to_nlm(rnlm, nlm_len_=None):
 # structure tensors, eigenframe, enhancement factors (host arrays)
 # ------------------------------------------------------------------------------------------
 
-def _nlm15(nlm):
-    """(N, >=15) complex -> Fortran-ordered (N, k) complex128 (only the l<=4 coefficients are read)"""
+def _nlm15(nlm, k=15):
+    """(N, >=k) complex -> Fortran-ordered (N, k) complex128 (only the first k coefficients are read: l<=4 for k=15,
+    l<=6 for 28, l<=8 for 45)"""
     a = np.asarray(nlm, dtype=np.complex128)
-    if a.ndim != 2 or a.shape[1] < 15:
-        raise ValueError("expected nlm of shape (N, nlm_len>=15), got %s" % (a.shape,))
-    return np.asfortranarray(a[:, :15])
+    if a.ndim != 2 or a.shape[1] < k:
+        raise ValueError("expected nlm of shape (N, nlm_len>=%d), got %s" % (k, a.shape))
+    return np.asfortranarray(a[:, :k])
 
 
 def a2_arr(nlm):
@@ -292,6 +293,40 @@ def a4_arr(nlm):
     N = x.shape[0]
     out = np.empty((N, 3, 3, 3, 3), dtype=np.float64, order="F")
     _lib.check(_lib.load().sfb_a4_arr(x.ctypes.data, N, N, out.ctypes.data))
+    return out
+
+
+def a6_arr(nlm):
+    """a6 of every node: (N,nlm_len) -> (N,3,3,3,3,3,3), needs L >= 6      reference per node: src/specfabpy.f90:601-608"""
+    _need_init()
+    x = _nlm15(nlm, 28)
+    N = x.shape[0]
+    out = np.empty((N,) + (3,) * 6, dtype=np.float64, order="F")
+    _lib.check(_lib.load().sfb_a6_arr(x.ctypes.data, N, N, out.ctypes.data))
+    return out
+
+
+def E_CAFFE_arr(nlm, eps, Emin, Emax, n_grain):
+    """E_CAFFE_arr(nlm (N,nlm_len), eps (N,3,3), Emin, Emax, n_grain) -> E (N,)     reference: src/specfabpy.f90:543-554"""
+    _need_init()
+    x = _nlm15(nlm, 45 if int(n_grain) == 3 else 15)
+    N = x.shape[0]
+    e = _farr(eps, np.float64, (3, 3))
+    if e.shape[0] != N:
+        raise ValueError("eps must have one 3x3 tensor per node")
+    out = np.empty(N, dtype=np.float64)
+    _lib.check(_lib.load().sfb_E_CAFFE_arr(x.ctypes.data, N, N, e.ctypes.data, float(Emin), float(Emax), int(n_grain), out.ctypes.data))
+    return out
+
+
+def pfJ_arr(nlm, Lmax=None):
+    """pole-figure J index of every node, truncated at Lmax (default L) -> (N,)     reference per node: src/specfabpy.f90:729-736"""
+    _need_init()
+    Lmax = _state["L"] if Lmax is None else int(Lmax)
+    x = _nlm15(nlm, (Lmax + 1) * (Lmax + 2) // 2)
+    N = x.shape[0]
+    out = np.empty(N, dtype=np.float64)
+    _lib.check(_lib.load().sfb_pfJ_arr(x.ctypes.data, N, N, Lmax, out.ctypes.data))
     return out
 
 
@@ -319,9 +354,10 @@ def eigframe_arr(M, plane="ij"):
 
 def Eij_tranisotropic_arr(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_status=False):
     """Eij_tranisotropic_arr(nlm (N,nlm_len), e1,e2,e3 (N,3), Eij_grain(2), alpha, n_grain) -> Eij (N,6)
-    reference: src/specfabpy.f90:474-486.  return_status adds the per-node SFB_ST_* flags."""
+    reference: src/specfabpy.f90:474-486.  return_status adds the per-node SFB_ST_* flags.
+    n_grain: 1, 3 (needs L >= 8) or -3."""
     _need_init()
-    x = _nlm15(nlm)
+    x = _nlm15(nlm, 45 if int(n_grain) == 3 else 15)
     N = x.shape[0]
     es = [_farr(e, np.float64, (3,)) for e in (e1, e2, e3)]
     g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
@@ -358,7 +394,7 @@ def Eij_eigenframe_arr(nlm, Eij_grain, alpha, n_grain, return_frame=False, retur
     """Fused a2 -> eigenframe -> Eij_tranisotropic (eigenenhancements) of every node -> Eij (N,6)
     [, ei (N,3,3), lami (N,3)] [, status].  Batches src/specfabpy/fenics/enhancementfactor.py:101-128."""
     _need_init()
-    x = _nlm15(nlm)
+    x = _nlm15(nlm, 45 if int(n_grain) == 3 else 15)
     N = x.shape[0]
     g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
     out = np.empty((N, 6), dtype=np.float64, order="F")
@@ -384,6 +420,21 @@ def a2(nlm):
 def a4(nlm):
     """reference: src/specfabpy.f90:592-599"""
     return np.ascontiguousarray(a4_arr(np.asarray(nlm)[None, :])[0])
+
+
+def a6(nlm):
+    """reference: src/specfabpy.f90:601-608"""
+    return np.ascontiguousarray(a6_arr(np.asarray(nlm)[None, :])[0])
+
+
+def E_CAFFE(nlm, eps, Emin, Emax, n_grain):
+    """reference: src/enhancementfactors.f90:301-331 (specfabpy E_CAFFE)"""
+    return float(E_CAFFE_arr(np.asarray(nlm)[None, :], np.asarray(eps)[None, :, :], Emin, Emax, n_grain)[0])
+
+
+def pfJ(nlm, Lmax=None):
+    """reference: src/specfabpy.f90:729-736"""
+    return float(pfJ_arr(np.asarray(nlm)[None, :], Lmax)[0])
 
 
 def eig(nlm):

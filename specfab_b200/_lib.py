@@ -50,6 +50,12 @@ SIGNATURES = {
     "sfb_eigframe_arr_dev": (C.c_int, [_P, _I64, _I64, C.c_char_p, _P, _P, _P]),
     "sfb_Eij_tranisotropic_arr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
     "sfb_Eij_tranisotropic_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P]),
+    "sfb_a6_arr": (C.c_int, [_P, _I64, _I64, _P]),
+    "sfb_a6_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "sfb_E_CAFFE_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_double, C.c_int, _P]),
+    "sfb_E_CAFFE_arr_dev": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_double, C.c_int, _P, _P]),
+    "sfb_pfJ_arr": (C.c_int, [_P, _I64, _I64, C.c_int, _P]),
+    "sfb_pfJ_arr_dev": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P]),
     "sfb_Eij_orthotropic_arr": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P]),
     "sfb_Eij_orthotropic_arr_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
     "sfb_Eij_eigenframe_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P]),

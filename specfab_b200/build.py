@@ -130,6 +130,7 @@ def generate(Ls):
     _write_if_changed(os.path.join(GEN, "registry.inc"), "\n".join(reg) + "\n")
     _write_if_changed(os.path.join(GEN, "tables.inc"), emit_tables.emit())
     _write_if_changed(os.path.join(GEN, "orth_tables.inc"), emit_tables.emit_orthotropic())
+    _write_if_changed(os.path.join(GEN, "moments_hi.inc"), emit_tables.emit_moments_hi())
     with open(os.path.join(GEN, "meta.json"), "w") as f:
         json.dump(metas, f, indent=1)
     return units, metas
@@ -143,7 +144,7 @@ def _deps_hash(src):
         tag = os.path.basename(src)[5:-3]
         files.append(os.path.join(GEN, "apply_%s.inc" % tag))
     else:
-        files += [os.path.join(GEN, "registry.inc"), os.path.join(GEN, "tables.inc"), os.path.join(GEN, "orth_tables.inc")]
+        files += [os.path.join(GEN, "registry.inc"), os.path.join(GEN, "tables.inc"), os.path.join(GEN, "orth_tables.inc"), os.path.join(GEN, "moments_hi.inc")]
     for f in files:
         h.update(open(f, "rb").read())
     h.update(" ".join(CFLAGS + ARCH).encode())
@@ -172,7 +173,7 @@ def build(Ls=None, jobs=None, verbose=False):
     jobs = jobs or max(1, (os.cpu_count() or 2))
     units, metas = generate(Ls)
     units = units + [os.path.join(CSRC, "sfb_api.cu"), os.path.join(CSRC, "sfb_fields.cu"), os.path.join(CSRC, "sfb_operators.cu"),
-                     os.path.join(CSRC, "sfb_orthotropic.cu")]
+                     os.path.join(CSRC, "sfb_orthotropic.cu"), os.path.join(CSRC, "sfb_fields_hi.cu")]
     objs = []
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
         for obj, dt, log in ex.map(lambda s: compile_one(s, verbose), units):

@@ -21,6 +21,13 @@ cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double*
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
                            long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_a6(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_eij3(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
+                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
+                            int* status, cudaStream_t st);
+cudaError_t sfb_launch_caffe(const double2* nlm, long long N, long long ld, const double* eps, long long lde, double Emin, double Emax,
+                             int n_grain, double* E, cudaStream_t st);
+cudaError_t sfb_launch_pfj(const double2* nlm, long long N, long long ld, int Lmax, double* J, cudaStream_t st);
 cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2* q2, long long ld2, const double2* q3, long long ld3,
                                 long long N, const double* e1, const double* e2, const double* e3, long long lde,
                                 const double* Eij_grain, int n_grain, double* Eij, long long ldo, cudaStream_t st);
@@ -300,10 +307,12 @@ void rheo_params(const double E[2], double n, int ef, double& cI, double& cM, do
 }
 int make_coef(const double* Eij_grain, double alpha, int n_grain, sfb::EijCoef& K) {
     if (!Eij_grain) return fail(SFB_EINVAL, "null Eij_grain");
-    if (n_grain != 1) return fail(SFB_EINVAL, "only n_grain = 1 is implemented (n'=3 Sachs needs a6/a8: SURVEY.md 8f-4)");
+    if (n_grain != 1 && n_grain != 3 && n_grain != -3) return fail(SFB_EINVAL, "unsupported n' (n_grain must be 1, 3 or -3)");
+    if (n_grain == 3 && g.L < 8) return fail(SFB_EINVAL, "Sachs homogenization with n'=3 requires L >= 8");
     rheo_params(Eij_grain, (double)n_grain, 1, K.sA, K.sB, K.sC);
     rheo_params(Eij_grain, (double)n_grain, -1, K.tA, K.tB, K.tC);
-    K.s_iso = 1 + 2.0 / 15 * K.sB + 2.0 / 3 * K.sC;
+    // n' = -3: numerator and isotropic denominator both carry I2 = tau:tau, which cancels (src/homogenizations.f90:105-109,209)
+    K.s_iso = n_grain == -3 ? 1.0 : 1 + 2.0 / 15 * K.sB + 2.0 / 3 * K.sC;
     K.t_iso = 1 + 2.0 / 15 * K.tB + 2.0 / 3 * K.tC;
     K.alpha = alpha;
     return SFB_OK;
@@ -404,7 +413,8 @@ int sfb_Eij_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, cons
     if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
     if (N == 0) return SFB_OK;
     if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
-    CK(sfb_launch_eij(reinterpret_cast<const double2*>(nlm), N, ld, e1, e2, e3, N, K, Eij, N, nullptr, nullptr, status, (cudaStream_t)stream));
+    CK((n_grain == 3 ? sfb_launch_eij3 : sfb_launch_eij)(reinterpret_cast<const double2*>(nlm), N, ld, e1, e2, e3, N, K, Eij, N, nullptr,
+                                                         nullptr, status, (cudaStream_t)stream));
     return SFB_OK;
 }
 int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
@@ -416,7 +426,7 @@ int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const do
     if (N == 0) return SFB_OK;
     if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
     DevTmp in, de, out, ds;
-    if ((rc = stage_rows(in, nlm, N, ld, 15))) return rc;
+    if ((rc = stage_rows(in, nlm, N, ld, n_grain == 3 ? 45 : 15))) return rc;
     CK(de.alloc((size_t)N * 9 * 8));
     CK(cudaMemcpy(de.as<double>(), e1, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(de.as<double>() + 3 * N, e2, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
@@ -428,6 +438,71 @@ int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const do
     if (rc) return rc;
     CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
     if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_a6_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a6, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (g.L < 6) return fail(SFB_EINVAL, "a6 requires L >= 6");
+    if (N && !a6) return fail(SFB_EINVAL, "null output");
+    CK(sfb_launch_a6(reinterpret_cast<const double2*>(nlm), N, ld, a6, N, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_a6_arr(const double* nlm, int64_t N, int64_t ld, double* a6) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (g.L < 6) return fail(SFB_EINVAL, "a6 requires L >= 6");
+    if (N == 0) return SFB_OK;
+    DevTmp in, out;
+    if ((rc = stage_rows(in, nlm, N, ld, 28))) return rc;
+    CK(out.alloc((size_t)N * 729 * 8));
+    if ((rc = sfb_a6_arr_dev(in.as<double>(), N, N, out.as<double>(), nullptr))) return rc;
+    CK(cudaMemcpy(a6, out.p, (size_t)N * 729 * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_E_CAFFE_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* eps, double Emin, double Emax, int n_grain, double* E,
+                        void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (n_grain == 3 && g.L < 8) return fail(SFB_EINVAL, "E_CAFFE with n'=3 requires L >= 8");
+    if (N && (!eps || !E)) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_caffe(reinterpret_cast<const double2*>(nlm), N, ld, eps, N, Emin, Emax, n_grain, E, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_E_CAFFE_arr(const double* nlm, int64_t N, int64_t ld, const double* eps, double Emin, double Emax, int n_grain, double* E) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (n_grain == 3 && g.L < 8) return fail(SFB_EINVAL, "E_CAFFE with n'=3 requires L >= 8");
+    if (N == 0) return SFB_OK;
+    if (!eps || !E) return fail(SFB_EINVAL, "null array");
+    DevTmp in, de, out;
+    if ((rc = stage_rows(in, nlm, N, ld, n_grain == 3 ? 45 : 15))) return rc;
+    CK(de.alloc((size_t)N * 9 * 8));
+    CK(cudaMemcpy(de.p, eps, (size_t)N * 9 * 8, cudaMemcpyHostToDevice));
+    CK(out.alloc((size_t)N * 8));
+    if ((rc = sfb_E_CAFFE_arr_dev(in.as<double>(), N, N, de.as<double>(), Emin, Emax, n_grain, out.as<double>(), nullptr))) return rc;
+    CK(cudaMemcpy(E, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_pfJ_arr_dev(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (Lmax < 0 || Lmax > g.L || (Lmax & 1)) return fail(SFB_EINVAL, "need even 0 <= Lmax <= L");
+    if (N && !J) return fail(SFB_EINVAL, "null output");
+    CK(sfb_launch_pfj(reinterpret_cast<const double2*>(nlm), N, ld, Lmax, J, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_pfJ_arr(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (Lmax < 0 || Lmax > g.L || (Lmax & 1)) return fail(SFB_EINVAL, "need even 0 <= Lmax <= L");
+    if (N == 0) return SFB_OK;
+    DevTmp in, out;
+    const int rows = (Lmax + 1) * (Lmax + 2) / 2;
+    if ((rc = stage_rows(in, nlm, N, ld, rows))) return rc;
+    CK(out.alloc((size_t)N * 8));
+    if ((rc = sfb_pfJ_arr_dev(in.as<double>(), N, N, Lmax, out.as<double>(), nullptr))) return rc;
+    CK(cudaMemcpy(J, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }
 int sfb_Eij_orthotropic_arr_dev(const double* nlm_1, int64_t ld1, const double* nlm_2, int64_t ld2, const double* nlm_3, int64_t ld3,
@@ -479,7 +554,8 @@ int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const d
     if (N == 0) return SFB_OK;
     if (!Eij) return fail(SFB_EINVAL, "null array");
     if ((ei == nullptr) != (lami == nullptr)) return fail(SFB_EINVAL, "ei and lami must both be given or both be NULL");
-    CK(sfb_launch_eij(reinterpret_cast<const double2*>(nlm), N, ld, nullptr, nullptr, nullptr, 0, K, Eij, N, ei, lami, status, (cudaStream_t)stream));
+    CK((n_grain == 3 ? sfb_launch_eij3 : sfb_launch_eij)(reinterpret_cast<const double2*>(nlm), N, ld, nullptr, nullptr, nullptr, 0, K, Eij,
+                                                         N, ei, lami, status, (cudaStream_t)stream));
     return SFB_OK;
 }
 int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
@@ -492,7 +568,7 @@ int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const doubl
     if (!Eij) return fail(SFB_EINVAL, "null array");
     if ((ei == nullptr) != (lami == nullptr)) return fail(SFB_EINVAL, "ei and lami must both be given or both be NULL");
     DevTmp in, out, o1, o2, ds;
-    if ((rc = stage_rows(in, nlm, N, ld, 15))) return rc;
+    if ((rc = stage_rows(in, nlm, N, ld, n_grain == 3 ? 45 : 15))) return rc;
     CK(out.alloc((size_t)N * 6 * 8));
     CK(o1.alloc((size_t)N * 9 * 8));
     CK(o2.alloc((size_t)N * 3 * 8));

@@ -5,27 +5,8 @@ namespace {
 
 constexpr int kBlock = 128;
 
-__device__ __forceinline__ void load_m_ge0(const double2* __restrict__ nlm, long long ld, long long p,
-                                           double2& n00, double2 n2[3], double2 n4[5]) {
-    n00 = nlm[p];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];     // n_2^m at 0-based index 3+m
-#pragma unroll
-    for (int m = 0; m < 5; ++m) n4[m] = nlm[(long long)(10 + m) * ld + p];    // n_4^m at 0-based index 10+m
-}
-
-__device__ __forceinline__ void a2_from(double2 n00, const double2 n2[3], double a[3][3]) {
-    double a2v[6];
-    sfb::ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
-    // src/moments.f90:37-44 returns f_ev_c2 directly (no Mandel round trip): undo the sqrt(2) scaling exactly
-    // by recomputing the off-diagonals from the same expressions
-    const double2 h1 = sfb::cdiv(n2[1], n00), h2 = sfb::cdiv(n2[2], n00);
-    const double s215 = 0.3651483716701107;
-    a[0][0] = a2v[0]; a[1][1] = a2v[1]; a[2][2] = a2v[2];
-    a[0][1] = a[1][0] = s215 * (-h2.y);
-    a[0][2] = a[2][0] = s215 * (-h1.x);
-    a[1][2] = a[2][1] = s215 * (h1.y);
-}
+using sfb::load_m_ge0;
+using sfb::a2_from;
 
 __global__ void __launch_bounds__(kBlock) a2_kernel(const double2* __restrict__ nlm, long long N, long long ld,
                                                     double* __restrict__ out, long long ldo) {

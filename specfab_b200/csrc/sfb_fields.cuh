@@ -149,6 +149,29 @@ __device__ __forceinline__ void eigframe(const double m[3][3], int plane, double
     }
 }
 
+// ---- node loads / a2 shared by the field kernels
+__device__ __forceinline__ void load_m_ge0(const double2* __restrict__ nlm, long long ld, long long p,
+                                           double2& n00, double2 n2[3], double2 n4[5]) {
+    n00 = nlm[p];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];     // n_2^m at 0-based index 3+m
+#pragma unroll
+    for (int m = 0; m < 5; ++m) n4[m] = nlm[(long long)(10 + m) * ld + p];    // n_4^m at 0-based index 10+m
+}
+
+__device__ __forceinline__ void a2_from(double2 n00, const double2 n2[3], double a[3][3]) {
+    double a2v[6];
+    sfb::ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
+    // src/moments.f90:37-44 returns f_ev_c2 directly (no Mandel round trip): undo the sqrt(2) scaling exactly
+    // by recomputing the off-diagonals from the same expressions
+    const double2 h1 = sfb::cdiv(n2[1], n00), h2 = sfb::cdiv(n2[2], n00);
+    const double s215 = 0.3651483716701107;
+    a[0][0] = a2v[0]; a[1][1] = a2v[1]; a[2][2] = a2v[2];
+    a[0][1] = a[1][0] = s215 * (-h2.y);
+    a[0][2] = a[2][0] = s215 * (-h1.x);
+    a[1][2] = a[2][1] = s215 * (h1.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Eij_tranisotropic, n'=1
 // ---------------------------------------------------------------------------------------------
@@ -222,8 +245,12 @@ __device__ __forceinline__ void potrs_lower(const double a[6][6], const double i
 }
 
 // Eij = (E11,E22,E33,E23,E13,E12) w.r.t. the rows of e[3][3].  returns status flags.
+// SACHS_GIVEN: the six Sachs ratios come from the caller (n'=3 closure, sfb_moments_hi.cuh); the Taylor part is
+// always the n'=1 solve with the caller's coefficients (src/homogenizations.f90:148).
+template <bool SACHS_GIVEN = false>
 __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3], const double2 n4[5],
-                                                 const double e[3][3], const EijCoef& K, double E[6]) {
+                                                 const double e[3][3], const EijCoef& K, double E[6],
+                                                 const double* Es_given = nullptr) {
     double a2v[6], a4p[21];
     ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
     ev_c4_mandel(n00, n2, n4, a4p);
@@ -290,6 +317,10 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
             }
         double tv[6];
         mat_to_vec(tau, tv);
+        double Es;
+        if (SACHS_GIVEN) {
+            Es = Es_given[q];
+        } else {
         // ---- Sachs (src/homogenizations.f90:88-91,115)
         double a4t_v[6], a4t[3][3];
 #pragma unroll
@@ -315,7 +346,8 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
                 eps[i][j] = ((1.0 * tau[i][j] - K.sA * a2tau * (i == j ? 1.0 : 0.0)) + K.sB * a4t[i][j]) + K.sC * (ac + ac2);
                 epsi[i][j] = K.s_iso * tau[i][j];
             }
-        const double Es = dinner22(eps, vw) / dinner22(epsi, vw);
+        Es = dinner22(eps, vw) / dinner22(epsi, vw);
+        }
         // ---- Taylor (src/homogenizations.f90:172-188)
         double x[6];
         if (info == 0) {

@@ -163,7 +163,7 @@ def test_taylor_fallback_and_status():
         nfb += rst == 1
     assert nfb > 0, "test did not exercise the fallback branch"
     with pytest.raises(sf.SpecfabB200Error):
-        sf.Eij_tranisotropic_arr(x, e[:, 0], e[:, 1], e[:, 2], GRAIN, ALPHA, 3)
+        sf.Eij_tranisotropic_arr(x, e[:, 0], e[:, 1], e[:, 2], GRAIN, ALPHA, 2)      # "unsupported n'" (src/homogenizations.f90:110-112)
 
 
 def test_moments_after_1000_steps():
@@ -281,3 +281,83 @@ def test_Eij_orthotropic_device_arrays():
     out = sf.Eij_orthotropic_arr_dev(dev(q1), dev(q2), None, dev(e1), dev(e2), dev(e3), OLIVINE, 0.0, 1)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().T, host)
+
+
+# ---------------------------------------------------------------------------------------------
+# a6 / a8 based fields: a6_arr, n'=3 Sachs, E_CAFFE, pfJ          
+# ---------------------------------------------------------------------------------------------
+def test_a6_parity():
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    x = random_states(L, 70, 51, True)
+    a6 = sf.a6_arr(x)
+    ref = np.array([orc.a6(v) for v in x])
+    assert a6.shape == (70,) + (3,) * 6
+    assert relerr_nodes(a6, ref).max() < 1e-13
+    assert np.array_equal(sf.a6(x[3]), a6[3])
+    assert np.array_equal(a6, a6.transpose(0, 2, 1, 3, 4, 6, 5))
+
+
+@pytest.mark.parametrize("n_grain", [3, -3])
+def test_Eij_tranisotropic_nonlinear_grains(n_grain):
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    N = 45
+    x = evolved_states(N, 61)
+    e1, e2, e3 = _frames(N, 62)
+    for grain, alpha in ((GRAIN, ALPHA), ((0.5, 20.0), 0.3)):
+        E, st = sf.Eij_tranisotropic_arr(x, e1, e2, e3, grain, alpha, n_grain, return_status=True)
+        ref = np.array([orc.Eij_tranisotropic(x[p], e1[p], e2[p], e3[p], grain, alpha, n_grain) for p in range(N)])
+        assert np.all(st == 0)
+        assert np.abs(E / ref - 1).max() < 1e-10
+    # fused eigenframe variant uses the same closure
+    Ef, ei, lami = sf.Eij_eigenframe_arr(x, GRAIN, ALPHA, n_grain, return_frame=True)
+    Eg = sf.Eij_tranisotropic_arr(x, ei[:, 0], ei[:, 1], ei[:, 2], GRAIN, ALPHA, n_grain)
+    assert np.abs(Ef / Eg - 1).max() < 1e-12
+    if n_grain == 3:          # isotropic pin (n' = -3 is not normalised by the reference)
+        iso = np.zeros((3, x.shape[1]), dtype=np.complex128); iso[:, 0] = 1 / np.sqrt(4 * np.pi)
+        assert np.abs(sf.Eij_tranisotropic_arr(iso, e1[:3], e2[:3], e3[:3], GRAIN, ALPHA, n_grain) - 1).max() < 1e-12
+
+
+def test_Eij_n3_needs_L8():
+    import specfab_b200 as sf
+    lm, n = sf.init(6)
+    x = np.zeros((2, n), dtype=np.complex128); x[:, 0] = 1 / np.sqrt(4 * np.pi)
+    e = np.tile(np.eye(3)[None], (2, 1, 1))
+    with pytest.raises((sf.SpecfabB200Error, ValueError)):
+        sf.Eij_tranisotropic_arr(x, e[:, 0], e[:, 1], e[:, 2], GRAIN, ALPHA, 3)
+    with pytest.raises(sf.SpecfabB200Error):
+        sf.Eij_tranisotropic_arr(x, e[:, 0], e[:, 1], e[:, 2], GRAIN, ALPHA, 2)
+    sf.init(L)
+
+
+@pytest.mark.parametrize("n_grain", [1, 3])
+def test_E_CAFFE_parity(n_grain):
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    N = 80
+    x = evolved_states(N, 71)
+    eps = random_tau(N, 72)
+    E = sf.E_CAFFE_arr(x, eps, 0.1, 10.0, n_grain)
+    ref = np.array([orc.E_CAFFE(x[p], eps[p], 0.1, 10.0, n_grain) for p in range(N)])
+    ok = np.isfinite(ref)
+    assert ok.sum() > N // 2 and np.array_equal(np.isfinite(E), ok)
+    assert np.abs(E[ok] / ref[ok] - 1).max() < 1e-10
+    assert (ref[ok] < 1).any() and (ref[ok] > 1).any()            # both branches of the Placidi law
+    assert sf.E_CAFFE(x[2], eps[2], 0.1, 10.0, n_grain) == E[2]
+
+
+def test_pfJ_parity():
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    x = random_states(L, 33, 81, False)
+    for Lmax in (None, 4, 0):
+        J = sf.pfJ_arr(x, Lmax)
+        ref = np.array([orc.pfJ(v, Lmax) for v in x])
+        assert np.abs(J / ref - 1).max() < 1e-14
+    with pytest.raises((sf.SpecfabB200Error, ValueError)):
+        sf.pfJ_arr(x, 10)

@@ -161,3 +161,50 @@ def test_orthotropic_enhancements_pins():
     assert abs(np.einsum("iijj", o.a4_joint(b, n)) - 1) < 1e-6
     # n_grain /= 1 is "silently 0" in the reference's forward rheology -> 0/0
     assert np.all(np.isnan(o.Eij_orthotropic(iso, iso, iso, e[0], e[1], e[2], (1, 1, 1, 1, 10, 1), 0.0, 3)))
+
+
+@pytest.mark.parametrize("tag,fn", [("c6", "a6"), ("c8", "a8")])
+def test_high_order_structure_tensors(tag, fn):
+    """src/moments.f90:220-236: coefficient tables of the unique a6 / a8 entries (tools/make_moment_tables.py) against
+    the numeric interpretation of all 729 / 6561 assignments of the reference bodies (tools/make_golden.py)"""
+    o.init(8)
+    for c in range(G["hi_nlm"].shape[0]):
+        r = getattr(o, fn)(G["hi_nlm"][c])
+        ref = G["hi_" + tag][c]
+        assert r.shape == ref.shape
+        assert np.abs(r - ref).max() < 5e-15 * np.abs(ref).max()
+
+
+def test_high_order_contractions_and_closures():
+    """a8 -> a6 -> a4 -> a2 by contraction (float32-constant accuracy; the a4 alias quirk shows up in exactly one
+    entry), delta function pins, isotropic n'=3 enhancements = 1"""
+    o.init(8)
+    from math import sqrt, pi
+    d = np.zeros(45, complex)
+    for l, j in ((0, 0), (2, 3), (4, 10), (6, 21), (8, 36)):
+        d[j] = sqrt((2 * l + 1) / (4 * pi))                  # delta function along z
+    assert abs(o.a8(d)[(2,) * 8] - 1) < 1e-7 and abs(o.a6(d)[(2,) * 6] - 1) < 1e-7
+    assert abs(o.pfJ(d) - sum(2 * l + 1 for l in range(0, 9, 2))) < 1e-12
+    x = np.zeros(45, complex); x[0] = 1 / sqrt(4 * pi)
+    rng = np.random.default_rng(1)
+    x[1:] = 0.02 * (rng.standard_normal(44) + 1j * rng.standard_normal(44))
+    lm = [(l, m) for l in range(0, 9, 2) for m in range(-l, l + 1)]
+    idx = {k: j for j, k in enumerate(lm)}
+    for (l, m), j in idx.items():
+        x[j] = x[j].real if m == 0 else ((-1) ** abs(m) * np.conj(x[idx[(l, -m)]]) if m < 0 else x[j])
+    A8, A6, A4, A2 = o.a8(x), o.a6(x), o.a4(x), o.a2(x)
+    assert np.abs(np.einsum("abcdefii", A8) - A6).max() < 1e-7
+    dev = np.abs(np.einsum("abcdii", A6) - A4)
+    assert np.argwhere(dev > 1e-7).tolist() == [[2, 1, 0, 1]]        # src/include/ev_c4__body.f90:78
+    assert np.abs(np.einsum("abii", A4) - A2).max() < 1e-7
+    iso = np.zeros(45, complex); iso[0] = 1 / sqrt(4 * pi)
+    e = np.eye(3)
+    for ng in (1, 3):
+        assert np.abs(o.Eij_tranisotropic(iso, e[0], e[1], e[2], (1, 1e3), 0.0125, ng) - 1).max() < 1e-12
+    # n' = -3 is not normalised by the reference: its isotropic denominator is I2*tau without the (1 + 2/15 cB + 2/3 cC) factor
+    cA, cB, cC = o.rheo_params_tranisotropic((1, 1e3), 3, -3.0, 1)
+    Es = 1 + 2 / 15 * cB + 2 / 3 * cC
+    assert np.abs(o.Eij_tranisotropic(iso, e[0], e[1], e[2], (1, 1e3), 0.0, -3) - Es).max() < 1e-12 * abs(Es)
+    S = np.diag([.5, .5, -1.])
+    assert abs(o.ev_D4(iso, S) - 1) < 1e-6 and abs(o.E_CAFFE(iso, S, 0.1, 10, 1) - 1) < 1e-12
+    assert abs(o.E_CAFFE(iso, S, 0.1, 10, 3) - 1) < 1e-6

@@ -170,6 +170,23 @@ for tag, fn, rank in (("v2", "ev_v2__body.f90", 2), ("v4", "ev_v4__body.f90", 4)
     orth["orth_" + tag] = res
 out.update(orth)
 
+# ---- 6th / 8th order structure tensors (linear in nlm, l <= 8, real(4) constants): numeric interpretation ----
+NH = 2
+hq = rng.standard_normal((NH, 45)) + 1j * rng.standard_normal((NH, 45))
+hq[:, 0] = 0.28 + 0.02 * rng.standard_normal(NH)
+out["hi_nlm"] = hq
+for tag, fn, rank in (("c6", "ev_c6__body.f90", 6), ("c8", "ev_c8__body.f90", 8)):
+    res = np.zeros((NH,) + (3,) * rank)
+    txt = rd("include", fn)
+    for c in range(NH):
+        env = {"Pi": PI, "n00": V("c8", hq[c, 0]), "n2m": cvec(hq[c, 1:6], -2), "n4m": cvec(hq[c, 6:15], -4),
+               "n6m": cvec(hq[c, 15:28], -6), "n8m": cvec(hq[c, 28:45], -8)}
+        run_body(txt, env, {"k": "r8", "ev": "r8"})
+        c0 = float(np.sqrt(4 * np.pi) * hq[c, 0].real)           # f_ev_c0 = REAL(sqrt(4*Pi)*n00)  (src/moments.f90:184-189)
+        for key, val in env["ev"].items():
+            res[(c,) + tuple(i - 1 for i in key)] = val.v * env["k"].v / c0      # ev = ev * k/f_ev_c0(n00)  (:226,:235)
+    out["hi_" + tag] = res
+
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "refbodies.npz")
 np.savez_compressed(dst, **out)
 print("wrote", os.path.normpath(dst), {k: v.shape for k, v in out.items()})
