@@ -155,6 +155,25 @@ int sfb_M_REG_arr(const double* eps, int64_t N, double* M);
 int sfb_M_REG_arr_dev(const double* eps, int64_t N, int64_t ld, double* M, void* stream);
 int sfb_M_CDRX(double* M /* [nlm_len*nlm_len] */);
 
+/* Reduced-form operators (src/reducedform.f90:76-120, specfabpy reduce_M src/specfabpy.f90:1066-1074): with rnlm the m >= 0
+ * coefficients,  d(rnlm)/dt = Mrr Re(rnlm) + Mri Im(rnlm) + i (Mir Re(rnlm) + Mii Im(rnlm)).  Every output is
+ * (N, rnlm_len, rnlm_len) real(8), Fortran order.  This is the form the FE couplers assemble
+ * (src/specfabpy/fenics/CPO.py:200-211, src/specfabpy/firedrake/ice.py:202-210).
+ *   sfb_reduce_M_arr           reduce an existing dense operator M (N, nlm_len, nlm_len), complex(8) or real(8)
+ *   sfb_M_LROT_reduced_arr     reduce_M(M_LROT(nlm, eps, omg, iota, zeta)) without materialising the dense M
+ *   sfb_M_DDRX_reduced_arr     reduce_M(M_DDRX(nlm, tau)), or of M_DDRX_src(tau) when src_only != 0 (nlm may then be NULL) */
+int sfb_reduce_M_arr(const double* M, int is_complex, int64_t N, double* Mrr, double* Mri, double* Mir, double* Mii);
+int sfb_reduce_M_arr_dev(const double* M, int is_complex, int64_t N, int64_t ld, double* Mrr, double* Mri, double* Mir, double* Mii,
+                         void* stream);
+int sfb_M_LROT_reduced_arr(const double* eps, const double* omg, int64_t N, double iota, double zeta,
+                           double* Mrr, double* Mri, double* Mir, double* Mii);
+int sfb_M_LROT_reduced_arr_dev(const double* eps, const double* omg, int64_t N, int64_t ld, double iota, double zeta,
+                               double* Mrr, double* Mri, double* Mir, double* Mii, void* stream);
+int sfb_M_DDRX_reduced_arr(const double* nlm, int64_t ld_nlm, const double* tau, int64_t N, int src_only,
+                           double* Mrr, double* Mri, double* Mir, double* Mii);
+int sfb_M_DDRX_reduced_arr_dev(const double* nlm, int64_t ld_nlm, const double* tau, int64_t N, int64_t ld, int src_only,
+                               double* Mrr, double* Mri, double* Mir, double* Mii, void* stream);
+
 /* apply_bounds(nlm): rescale the l=2 / l=4 blocks whose power spectrum exceeds the delta-function bound
  *                                            src/specfabpy.f90:764-771, src/dynamics.f90:530-557 */
 int sfb_apply_bounds_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld);

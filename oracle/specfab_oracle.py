@@ -768,6 +768,59 @@ def Eij_tranisotropic(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_status=
 
 
 # ---------------------------------------------------------------------------------------------
+# reduced form (src/reducedform.f90)
+# ---------------------------------------------------------------------------------------------
+
+def rlm_list():
+    """(l, m >= 0) of the reduced state vector, src/reducedform.f90:48"""
+    L, _ = _L()
+    return [(l, m) for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+
+
+def I_all():
+    """0-based positions of the m >= 0 coefficients in nlm, src/reducedform.f90:35"""
+    return np.array([l * (l + 1) // 2 + m for l, m in rlm_list()])
+
+
+def nlm_to_rnlm(nlm):
+    """src/reducedform.f90:172-182"""
+    return np.asarray(nlm, dtype=np.complex128)[I_all()]
+
+
+def rnlm_to_nlm(rnlm):
+    """src/reducedform.f90:160-170: n_l^-m = (-1)^m conj(n_l^m)"""
+    L, n = _L()
+    out = np.zeros(n, dtype=np.complex128)
+    for (l, m), v in zip(rlm_list(), np.asarray(rnlm, dtype=np.complex128)):
+        out[l * (l + 1) // 2 + m] = v
+        if m:
+            out[l * (l + 1) // 2 - m] = (-1) ** m * np.conj(v)
+    return out
+
+
+def reduce_M(M):
+    """src/reducedform.f90:76-120 -> (Mrr, Mri, Mir, Mii) with
+    d(rnlm)/dt = Mrr Re(rnlm) + Mri Im(rnlm) + i (Mir Re(rnlm) + Mii Im(rnlm))"""
+    M = np.asarray(M, dtype=np.complex128)
+    ia = I_all()
+    r = len(ia)
+    Mrr = np.zeros((r, r)); Mri = np.zeros((r, r)); Mir = np.zeros((r, r)); Mii = np.zeros((r, r))
+    for jj, (l, m) in enumerate(rlm_list()):
+        jp = ia[jj]
+        jn = jp - 2 * m
+        Vp, Qp = M[ia, jp].real, M[ia, jp].imag
+        Vn, Qn = M[ia, jn].real, M[ia, jn].imag
+        s = 1 if m % 2 == 0 else -1
+        if jp == jn:
+            s = 0
+        Mrr[:, jj] += Vp + s * Vn
+        Mri[:, jj] += -Qp + s * Qn
+        Mir[:, jj] += Qp + s * Qn
+        Mii[:, jj] += Vp - s * Vn
+    return Mrr, Mri, Mir, Mii
+
+
+# ---------------------------------------------------------------------------------------------
 # time stepping (src/dynamics.f90:108; src/specfabpy/integrator.py:73-77)
 # ---------------------------------------------------------------------------------------------
 

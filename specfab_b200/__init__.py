@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
-__all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
+__all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "a6", "a6_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
@@ -170,6 +170,56 @@ def M_REG_arr(eps):
     M = np.empty((N, n, n), dtype=np.float64, order="F")
     _lib.check(_lib.load().sfb_M_REG_arr(e.ctypes.data, N, M.ctypes.data))
     return M
+
+
+def _four(N):
+    r = rnlm_len()
+    return [np.empty((N, r, r), dtype=np.float64, order="F") for _ in range(4)]
+
+
+def reduce_M_arr(M):
+    """reduce_M of every node: dense M (N,nlm_len,nlm_len) complex128 or float64 -> (Mrr, Mri, Mir, Mii), each
+    (N,rnlm_len,rnlm_len)            reference per node: src/specfabpy.f90:1066-1074, src/reducedform.f90:76-120"""
+    n = _need_init()
+    M = np.asarray(M)
+    cplx = np.iscomplexobj(M)
+    m = _farr(M, np.complex128 if cplx else np.float64, (n, n))
+    N = m.shape[0]
+    o = _four(N)
+    _lib.check(_lib.load().sfb_reduce_M_arr(m.ctypes.data, int(cplx), N, *[x.ctypes.data for x in o]))
+    return tuple(o)
+
+
+def reduce_M(M, rnlm_len_=None):
+    """reference: src/specfabpy.f90:1066-1074 -> (Mrr, Mri, Mir, Mii)"""
+    return tuple(np.ascontiguousarray(x[0]) for x in reduce_M_arr(np.asarray(M)[None]))
+
+
+def M_LROT_reduced_arr(eps, omg, iota, zeta):
+    """reduce_M(M_LROT) of every node without materialising the dense operator -> (Mrr, Mri, Mir, Mii)
+    (what src/specfabpy/fenics/CPO.py:200-211 builds per node)"""
+    _need_init()
+    e, w = _farr(eps, np.float64, (3, 3)), _farr(omg, np.float64, (3, 3))
+    N = e.shape[0]
+    o = _four(N)
+    _lib.check(_lib.load().sfb_M_LROT_reduced_arr(e.ctypes.data, w.ctypes.data, N, float(iota), float(zeta), *[x.ctypes.data for x in o]))
+    return tuple(o)
+
+
+def M_DDRX_reduced_arr(nlm, tau, src_only=False):
+    """reduce_M(M_DDRX(nlm, tau)) (or of M_DDRX_src(tau) with src_only=True) of every node -> (Mrr, Mri, Mir, Mii)"""
+    n = _need_init()
+    t = _farr(tau, np.float64, (3, 3))
+    N = t.shape[0]
+    x = None
+    if not src_only:
+        x = np.asfortranarray(np.asarray(nlm, dtype=np.complex128))
+        if x.shape != (N, n):
+            raise ValueError("nlm must have shape (N, nlm_len)")
+    o = _four(N)
+    _lib.check(_lib.load().sfb_M_DDRX_reduced_arr(x.ctypes.data if x is not None else None, N, t.ctypes.data, N, int(bool(src_only)),
+                                                  *[y.ctypes.data for y in o]))
+    return tuple(o)
 
 
 def M_LROT(nlm, eps, omg, iota, zeta):

@@ -28,6 +28,11 @@ cudaError_t sfb_launch_eij3(const double2* nlm, long long N, long long ld, const
 cudaError_t sfb_launch_caffe(const double2* nlm, long long N, long long ld, const double* eps, long long lde, double Emin, double Emax,
                              int n_grain, double* E, cudaStream_t st);
 cudaError_t sfb_launch_pfj(const double2* nlm, long long N, long long ld, int Lmax, double* J, cudaStream_t st);
+cudaError_t sfb_launch_mexport_reduced(int mode, int L, const double* a33, const double* b33, const double2* nlm, long long ldn,
+                                       long long N, long long ld, double iota, double zeta, double* Mrr, double* Mri, double* Mir,
+                                       double* Mii, cudaStream_t st);
+cudaError_t sfb_launch_reduce_dense(const double* M, int is_complex, int L, long long N, long long ldi, double* Mrr, double* Mri,
+                                    double* Mir, double* Mii, cudaStream_t st);
 cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2* q2, long long ld2, const double2* q3, long long ld3,
                                 long long N, const double* e1, const double* e2, const double* e3, long long lde,
                                 const double* Eij_grain, int n_grain, double* Eij, long long ldo, cudaStream_t st);
@@ -632,6 +637,83 @@ int sfb_M_DDRX_arr(const double* nlm, int64_t ldn, const double* tau, int64_t N,
 }
 int sfb_M_DDRX_arr_dev(const double* nlm, int64_t ldn, const double* tau, int64_t N, int64_t ld, double* M, void* stream) {
     return mexport_dev(2, tau, nullptr, nlm, ldn, N, ld, 0, 0, M, stream);
+}
+// ---- reduced-form operators (src/reducedform.f90:76-120)
+static int mreduced_dev(int mode, const double* a33, const double* b33, const double* nlm, int64_t ldn, int64_t N, int64_t ld,
+                        double iota, double zeta, double* Mrr, double* Mri, double* Mir, double* Mii, void* stream) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    if (N == 0) return SFB_OK;
+    if (!a33 || !Mrr || !Mri || !Mir || !Mii || (mode == 0 && !b33) || (mode == 2 && (!nlm || ldn < N))) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_mexport_reduced(mode, g.L, a33, b33, reinterpret_cast<const double2*>(nlm), ldn, N, ld, iota, zeta, Mrr, Mri, Mir, Mii,
+                                  (cudaStream_t)stream));
+    return SFB_OK;
+}
+static int mreduced_host(int mode, const double* a33, const double* b33, const double* nlm, int64_t ldn, int64_t N, double iota,
+                         double zeta, double* Mrr, double* Mri, double* Mir, double* Mii) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (N == 0) return SFB_OK;
+    if (!a33 || !Mrr || !Mri || !Mir || !Mii || (mode == 0 && !b33) || (mode == 2 && !nlm)) return fail(SFB_EINVAL, "null array");
+    DevTmp da, db, dn, dm;
+    int rc;
+    CK(da.alloc((size_t)N * 72));
+    CK(cudaMemcpy(da.p, a33, (size_t)N * 72, cudaMemcpyHostToDevice));
+    if (mode == 0) { CK(db.alloc((size_t)N * 72)); CK(cudaMemcpy(db.p, b33, (size_t)N * 72, cudaMemcpyHostToDevice)); }
+    if (mode == 2 && (rc = stage_rows(dn, nlm, N, ldn, 15))) return rc;
+    const int r = sfb_rnlm_len();
+    const size_t one = (size_t)N * r * r;
+    CK(dm.alloc(4 * one * 8));
+    double* o = dm.as<double>();
+    rc = mreduced_dev(mode, da.as<double>(), db.as<double>(), dn.as<double>(), N, N, N, iota, zeta, o, o + one, o + 2 * one, o + 3 * one, nullptr);
+    if (rc) return rc;
+    double* dst[4] = {Mrr, Mri, Mir, Mii};
+    for (int q = 0; q < 4; ++q) CK(cudaMemcpy(dst[q], o + q * one, one * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_M_LROT_reduced_arr(const double* eps, const double* omg, int64_t N, double iota, double zeta,
+                           double* Mrr, double* Mri, double* Mir, double* Mii) {
+    return mreduced_host(0, eps, omg, nullptr, 0, N, iota, zeta, Mrr, Mri, Mir, Mii);
+}
+int sfb_M_LROT_reduced_arr_dev(const double* eps, const double* omg, int64_t N, int64_t ld, double iota, double zeta,
+                               double* Mrr, double* Mri, double* Mir, double* Mii, void* stream) {
+    return mreduced_dev(0, eps, omg, nullptr, 0, N, ld, iota, zeta, Mrr, Mri, Mir, Mii, stream);
+}
+int sfb_M_DDRX_reduced_arr(const double* nlm, int64_t ldn, const double* tau, int64_t N, int src_only,
+                           double* Mrr, double* Mri, double* Mir, double* Mii) {
+    return mreduced_host(src_only ? 1 : 2, tau, nullptr, nlm, ldn, N, 0, 0, Mrr, Mri, Mir, Mii);
+}
+int sfb_M_DDRX_reduced_arr_dev(const double* nlm, int64_t ldn, const double* tau, int64_t N, int64_t ld, int src_only,
+                               double* Mrr, double* Mri, double* Mir, double* Mii, void* stream) {
+    return mreduced_dev(src_only ? 1 : 2, tau, nullptr, nlm, ldn, N, ld, 0, 0, Mrr, Mri, Mir, Mii, stream);
+}
+int sfb_reduce_M_arr_dev(const double* M, int is_complex, int64_t N, int64_t ld, double* Mrr, double* Mri, double* Mir, double* Mii,
+                         void* stream) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    if (N == 0) return SFB_OK;
+    if (!M || !Mrr || !Mri || !Mir || !Mii) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_reduce_dense(M, is_complex, g.L, N, ld, Mrr, Mri, Mir, Mii, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_reduce_M_arr(const double* M, int is_complex, int64_t N, double* Mrr, double* Mri, double* Mir, double* Mii) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (N == 0) return SFB_OK;
+    if (!M || !Mrr || !Mri || !Mir || !Mii) return fail(SFB_EINVAL, "null array");
+    DevTmp di, dm;
+    const size_t ibytes = (size_t)N * g.n * g.n * (is_complex ? 16 : 8);
+    CK(di.alloc(ibytes));
+    CK(cudaMemcpy(di.p, M, ibytes, cudaMemcpyHostToDevice));
+    const int r = sfb_rnlm_len();
+    const size_t one = (size_t)N * r * r;
+    CK(dm.alloc(4 * one * 8));
+    double* o = dm.as<double>();
+    int rc = sfb_reduce_M_arr_dev(di.as<double>(), is_complex, N, N, o, o + one, o + 2 * one, o + 3 * one, nullptr);
+    if (rc) return rc;
+    double* dst[4] = {Mrr, Mri, Mir, Mii};
+    for (int q = 0; q < 4; ++q) CK(cudaMemcpy(dst[q], o + q * one, one * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
 }
 int sfb_M_REG_arr_dev(const double* eps, int64_t N, int64_t ld, double* M, void* stream) {
     if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");

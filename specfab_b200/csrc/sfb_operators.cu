@@ -38,11 +38,36 @@ void build_dense() {
 }
 inline double T(int t, int i, int j, int k) { return g_dense[t][((size_t)i * kNMax + j) * kNCat + k]; }
 
+// one structurally non-zero entry (ii,jj) of the reduced operators (src/reducedform.f90:76-120): built from the
+// full-form entries M(I_all(ii), +m_jj) [zp] and M(I_all(ii), -m_jj) [zn] (index into the SfbNz list, -1 = zero)
+struct SfbRz {
+    int ii, jj, s, zp, zn;
+};
+
 struct DevLists {
     int L = 0;
     SfbNz *lrot = nullptr, *ddrx = nullptr;
-    int n_lrot = 0, n_ddrx = 0;
+    SfbRz *rlrot = nullptr, *rddrx = nullptr;
+    int n_lrot = 0, n_ddrx = 0, n_rlrot = 0, n_rddrx = 0;
 } g_lists[64];
+
+void reduced_list(int L, const std::vector<SfbNz>& nz, std::vector<SfbRz>& out) {
+    const int n = (L + 1) * (L + 2) / 2;
+    std::vector<int> where((size_t)n * n, -1);
+    for (size_t z = 0; z < nz.size(); ++z) where[(size_t)nz[z].i * n + nz[z].j] = (int)z;
+    int ii = 0;
+    for (int li = 0; li <= L; li += 2)
+        for (int mi = 0; mi <= li; ++mi, ++ii) {
+            const int ip = li * (li + 1) / 2 + mi;
+            int jj = 0;
+            for (int lj = 0; lj <= L; lj += 2)
+                for (int mj = 0; mj <= lj; ++mj, ++jj) {
+                    const int jp = lj * (lj + 1) / 2 + mj, jn = jp - 2 * mj;
+                    SfbRz r{ii, jj, mj == 0 ? 0 : ((mj & 1) ? -1 : 1), where[(size_t)ip * n + jp], where[(size_t)ip * n + jn]};
+                    if (r.zp >= 0 || r.zn >= 0) out.push_back(r);
+                }
+        }
+}
 
 // real(4) constants of src/dynamics.f90:79-86 promoted to double
 const double SQRT3_F = 0x1.bb67aep+0, S56 = 0x1.d363d2p-1, S23 = 0x1.a20bd8p-1, S32 = 0x1.3988e2p+0;
@@ -102,16 +127,12 @@ enum { SC_C0 = 0, SC_LAM = 1, SC_RM = 2, SC_G0 = 3, SC_TAUV = 4, SC_TSQV = 10, S
 #include "sfb_step_common.cuh"
 
 // mode 0: M_LROT(eps, omg, iota, zeta)   mode 1: M_DDRX_src(tau)   mode 2: M_DDRX(nlm, tau)
-__global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNz* __restrict__ nz, int nnz, int n,
-                                                           const double* __restrict__ a33, const double* __restrict__ b33,
-                                                           const double2* __restrict__ nlm, long long ldn, long long N, long long ld,
-                                                           double iota, double zeta, double2* __restrict__ M, long long ldm) {
-    __shared__ double2 f[kNF][kTN];
-    const int t = threadIdx.x;
-    const long long p = (long long)blockIdx.x * kTN + t;
-    const bool ok = p < N;
+// forcing coefficients of node p into f[.][t]; returns <D> (mode 2)
+__device__ __forceinline__ double mexport_forcing(int mode, double2 (*f)[kTN], int t, long long p,
+                                                  const double* __restrict__ a33, const double* __restrict__ b33,
+                                                  const double2* __restrict__ nlm, long long ldn, long long ld, double iota, double zeta) {
     double davg = 0.0;
-    if (ok) {
+    {
         if (mode == 0) {
             // reference reads eps / omg entries directly: quad_rr(iota*eps + zetanorm*eps^2), quad_tp(omg)
             double e[3][3], w[3][3], sq[3][3], E[3][3];
@@ -169,17 +190,89 @@ __global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNz
             }
         }
     }
-    if (!ok) return;
+    return davg;
+}
+
+__device__ __forceinline__ double2 nz_value(const SfbNz& e, const double2 (*f)[kTN], int t, int mode, double davg) {
+    double2 v = make_double2(0.0, 0.0);
+    for (int q = 0; q < e.nt; ++q) {
+        const double2 ff = f[e.fidx[q]][t];
+        v.x = fma(e.c[q], ff.x, v.x);
+        v.y = fma(e.c[q], ff.y, v.y);
+    }
+    if (mode == 2 && e.i == e.j) v.x -= davg;
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNz* __restrict__ nz, int nnz, int n,
+                                                           const double* __restrict__ a33, const double* __restrict__ b33,
+                                                           const double2* __restrict__ nlm, long long ldn, long long N, long long ld,
+                                                           double iota, double zeta, double2* __restrict__ M, long long ldm) {
+    __shared__ double2 f[kNF][kTN];
+    const int t = threadIdx.x;
+    const long long p = (long long)blockIdx.x * kTN + t;
+    if (p >= N) return;
+    const double davg = mexport_forcing(mode, f, t, p, a33, b33, nlm, ldn, ld, iota, zeta);
     for (int z = blockIdx.y; z < nnz; z += gridDim.y) {
         const SfbNz e = nz[z];
-        double2 v = make_double2(0.0, 0.0);
-        for (int q = 0; q < e.nt; ++q) {
-            const double2 ff = f[e.fidx[q]][t];
-            v.x = fma(e.c[q], ff.x, v.x);
-            v.y = fma(e.c[q], ff.y, v.y);
+        M[((long long)e.i + (long long)n * e.j) * ldm + p] = nz_value(e, f, t, mode, davg);
+    }
+}
+
+// the same operators written directly in reduced form (Mrr, Mri, Mir, Mii each (N, r, r) real), src/reducedform.f90:76-120
+__global__ void __launch_bounds__(kThreads) mexport_reduced_kernel(int mode, const SfbNz* __restrict__ nz, const SfbRz* __restrict__ rz,
+                                                                   int nrz, int r, const double* __restrict__ a33,
+                                                                   const double* __restrict__ b33, const double2* __restrict__ nlm,
+                                                                   long long ldn, long long N, long long ld, double iota, double zeta,
+                                                                   double* __restrict__ Mrr, double* __restrict__ Mri,
+                                                                   double* __restrict__ Mir, double* __restrict__ Mii, long long ldm) {
+    __shared__ double2 f[kNF][kTN];
+    const int t = threadIdx.x;
+    const long long p = (long long)blockIdx.x * kTN + t;
+    if (p >= N) return;
+    const double davg = mexport_forcing(mode, f, t, p, a33, b33, nlm, ldn, ld, iota, zeta);
+    for (int z = blockIdx.y; z < nrz; z += gridDim.y) {
+        const SfbRz e = rz[z];
+        const double2 vp = e.zp >= 0 ? nz_value(nz[e.zp], f, t, mode, davg) : make_double2(0.0, 0.0);
+        const double2 vn = e.zn >= 0 ? nz_value(nz[e.zn], f, t, mode, davg) : make_double2(0.0, 0.0);
+        const long long o = ((long long)e.ii + (long long)r * e.jj) * ldm + p;
+        const double s = (double)e.s;
+        Mrr[o] = vp.x + s * vn.x;
+        Mri[o] = -vp.y + s * vn.y;
+        Mir[o] = vp.y + s * vn.y;
+        Mii[o] = vp.x - s * vn.x;
+    }
+}
+
+// reduce_M on an existing dense operator M (N, n, n), complex or real; blockIdx.y = reduced entry (ii + r*jj)
+__global__ void __launch_bounds__(kThreads) reduce_dense_kernel(const double* __restrict__ M, int is_complex, int L, long long N,
+                                                                long long ldi, double* __restrict__ Mrr, double* __restrict__ Mri,
+                                                                double* __restrict__ Mir, double* __restrict__ Mii, long long ldo) {
+    const long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= N) return;
+    const int n = (L + 1) * (L + 2) / 2, r = (L + 2) * (L + 2) / 4;
+    for (int z = blockIdx.y; z < r * r; z += gridDim.y) {
+        const int ii = z % r, jj = z / r;
+        int li = 0, lj = 0;
+        while ((li / 2 + 1) * (li / 2 + 1) <= ii) li += 2;          // reduced index of (l, m) is (l/2)^2 + m
+        while ((lj / 2 + 1) * (lj / 2 + 1) <= jj) lj += 2;
+        const int mi = ii - (li / 2) * (li / 2), mj = jj - (lj / 2) * (lj / 2);
+        const int ip = li * (li + 1) / 2 + mi, jp = lj * (lj + 1) / 2 + mj, jn = jp - 2 * mj;
+        double2 vp, vn;
+        if (is_complex) {
+            const double2* Mc = reinterpret_cast<const double2*>(M);
+            vp = Mc[((long long)ip + (long long)n * jp) * ldi + p];
+            vn = Mc[((long long)ip + (long long)n * jn) * ldi + p];
+        } else {
+            vp = make_double2(M[((long long)ip + (long long)n * jp) * ldi + p], 0.0);
+            vn = make_double2(M[((long long)ip + (long long)n * jn) * ldi + p], 0.0);
         }
-        if (mode == 2 && e.i == e.j) v.x -= davg;
-        M[((long long)e.i + (long long)n * e.j) * ldm + p] = v;
+        const double s = mj == 0 ? 0.0 : ((mj & 1) ? -1.0 : 1.0);
+        const long long o = (long long)z * ldo + p;
+        Mrr[o] = vp.x + s * vn.x;
+        Mri[o] = -vp.y + s * vn.y;
+        Mir[o] = vp.y + s * vn.y;
+        Mii[o] = vp.x - s * vn.x;
     }
 }
 
@@ -205,9 +298,17 @@ cudaError_t sfb_ops_prepare(int L) {
     if (d.L == L) return cudaSuccess;
     std::vector<SfbNz> a, b;
     merge_lists(L, a, b);
-    cudaFree(d.lrot); cudaFree(d.ddrx);
+    std::vector<SfbRz> ra, rb;
+    reduced_list(L, a, ra);
+    reduced_list(L, b, rb);
+    cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx);
     d = DevLists();
     cudaError_t e;
+    if ((e = cudaMalloc(&d.rlrot, ra.size() * sizeof(SfbRz))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d.rddrx, rb.size() * sizeof(SfbRz))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.rlrot, ra.data(), ra.size() * sizeof(SfbRz), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.rddrx, rb.data(), rb.size() * sizeof(SfbRz), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    d.n_rlrot = (int)ra.size(); d.n_rddrx = (int)rb.size();
     if ((e = cudaMalloc(&d.lrot, a.size() * sizeof(SfbNz))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d.ddrx, b.size() * sizeof(SfbNz))) != cudaSuccess) return e;
     if ((e = cudaMemcpy(d.lrot, a.data(), a.size() * sizeof(SfbNz), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -217,7 +318,7 @@ cudaError_t sfb_ops_prepare(int L) {
 }
 
 void sfb_ops_release() {
-    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); d = DevLists(); }
+    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); d = DevLists(); }
 }
 
 // M must be zero-filled by the caller side of the launcher (done here with cudaMemsetAsync)
@@ -235,6 +336,36 @@ cudaError_t sfb_launch_mexport(int mode, int L, const double* a33, const double*
     const int nnz = mode == 0 ? d.n_lrot : d.n_ddrx;
     dim3 grid((unsigned)((N + kTN - 1) / kTN), (unsigned)std::min(nnz, 64));
     mexport_kernel<<<grid, kThreads, 0, st>>>(mode, nz, nnz, n, a33, b33, nlm, ldn, N, ld, iota, zeta, M, N);
+    return cudaGetLastError();
+}
+
+cudaError_t sfb_launch_mexport_reduced(int mode, int L, const double* a33, const double* b33, const double2* nlm, long long ldn,
+                                       long long N, long long ld, double iota, double zeta, double* Mrr, double* Mri, double* Mir,
+                                       double* Mii, cudaStream_t st) {
+    cudaError_t e = sfb_ops_prepare(L);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const DevLists& d = g_lists[dev & 63];
+    const int r = (L + 2) * (L + 2) / 4;
+    double* outs[4] = {Mrr, Mri, Mir, Mii};
+    for (double* o : outs)
+        if ((e = cudaMemsetAsync(o, 0, (size_t)N * r * r * sizeof(double), st)) != cudaSuccess) return e;
+    if (N <= 0) return cudaSuccess;
+    const SfbNz* nz = mode == 0 ? d.lrot : d.ddrx;
+    const SfbRz* rz = mode == 0 ? d.rlrot : d.rddrx;
+    const int nrz = mode == 0 ? d.n_rlrot : d.n_rddrx;
+    dim3 grid((unsigned)((N + kTN - 1) / kTN), (unsigned)std::min(nrz, 64));
+    mexport_reduced_kernel<<<grid, kThreads, 0, st>>>(mode, nz, rz, nrz, r, a33, b33, nlm, ldn, N, ld, iota, zeta, Mrr, Mri, Mir, Mii, N);
+    return cudaGetLastError();
+}
+
+cudaError_t sfb_launch_reduce_dense(const double* M, int is_complex, int L, long long N, long long ldi, double* Mrr, double* Mri,
+                                    double* Mir, double* Mii, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const int r = (L + 2) * (L + 2) / 4;
+    dim3 grid((unsigned)((N + kThreads - 1) / kThreads), (unsigned)std::min(r * r, 256));
+    reduce_dense_kernel<<<grid, kThreads, 0, st>>>(M, is_complex, L, N, ldi, Mrr, Mri, Mir, Mii, N);
     return cudaGetLastError();
 }
 

@@ -71,3 +71,41 @@ def test_nlm_LROT_integrator():
     got = sf.nlm_LROT(nlm0, 0.02, Nt, D, W, 1.0)
     ref = orc.nlm_LROT(nlm0, 0.02, Nt, D, W, 1.0)
     assert np.abs(got - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("L", [4, 8, 12])
+def test_reduced_operators(L):
+    """src/reducedform.f90:76-120: Mrr, Mri, Mir, Mii written directly, and reduce_M of a dense operator"""
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    N = 7
+    ug = random_ugrad(N, 40 + L)
+    tau = random_tau(N, 50 + L)
+    x = random_states(L, N, 60 + L, True)
+    D = (ug + ug.transpose(0, 2, 1)) / 2
+    W = (ug - ug.transpose(0, 2, 1)) / 2
+    r = sf.rnlm_len()
+    cases = [(sf.M_LROT_reduced_arr(D, W, 0.8, 0.25), lambda p: orc.M_LROT(D[p], W[p], 0.8, 0.25)),
+             (sf.M_DDRX_reduced_arr(x, tau), lambda p: orc.M_DDRX(x[p], tau[p])),
+             (sf.M_DDRX_reduced_arr(None, tau, src_only=True), lambda p: orc.M_DDRX_src(tau[p])),
+             (sf.reduce_M_arr(sf.M_REG_arr(D)), lambda p: orc.M_REG(D[p])),
+             (sf.reduce_M_arr(sf.M_LROT_arr(D, W, 0.8, 0.25)), lambda p: orc.M_LROT(D[p], W[p], 0.8, 0.25))]
+    for got, ref_of in cases:
+        assert all(g.shape == (N, r, r) for g in got)
+        for p in range(N):
+            Mfull = ref_of(p)
+            ref = orc.reduce_M(Mfull)
+            scale = np.abs(Mfull).max()
+            for g, rf in zip(got, ref):
+                assert np.abs(g[p] - rf).max() < 1e-13 * scale
+    # the reduced operators reproduce the full tendency on a physical state
+    Mrr, Mri, Mir, Mii = sf.M_LROT_reduced_arr(D, W, 1.0, 0.0)
+    rn = sf.nlm_to_rnlm_arr(x)
+    drn = np.einsum("pij,pj->pi", Mrr, rn.real) + np.einsum("pij,pj->pi", Mri, rn.imag) \
+        + 1j * (np.einsum("pij,pj->pi", Mir, rn.real) + np.einsum("pij,pj->pi", Mii, rn.imag))
+    dn = np.einsum("pij,pj->pi", sf.M_LROT_arr(D, W, 1.0, 0.0), x)
+    assert np.abs(drn - sf.nlm_to_rnlm_arr(dn)).max() < 1e-13 * np.abs(dn).max()
+    # scalar form with the reference's signature
+    one = sf.reduce_M(sf.M_LROT(x[0], D[0], W[0], 1.0, 0.0), r)
+    assert all(np.array_equal(a, b[0]) for a, b in zip(one, (Mrr, Mri, Mir, Mii)))
