@@ -123,6 +123,11 @@ int sfb_E_CAFFE_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* 
  * src/idealstate.f90:111-124 */
 int sfb_pfJ_arr(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J);
 int sfb_pfJ_arr_dev(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J, void* stream);
+/* State ingest: a2 (N,3,3) -> nlm (N,6);  a4 (N,3,3,3,3) -> nlm (N,15);  a6 (N,3^6) -> nlm (N,28)   (rank = 2, 4, 6)
+ *                                            src/specfabpy.f90:619-647, src/moments.f90:68-92.
+ * The output holds the l <= rank coefficients; the caller embeds them in a longer state (higher l = 0). */
+int sfb_ai_to_nlm_arr(int rank, const double* a, int64_t N, double* nlm);
+int sfb_ai_to_nlm_arr_dev(int rank, const double* a, int64_t N, int64_t ld, double* nlm, int64_t ld_nlm, void* stream);
 /* Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3 (N,nlm_len), e1,e2,e3 (N,3), Eij_grain(6), alpha, n_grain) -> Eij(N,6)
  *                                            src/specfabpy.f90:488-500, src/enhancementfactors.f90:134-189.
  * Orthotropic grains (olivine): nlm_1..3 are the distributions of the slip-system axes (b, n, v); where

@@ -572,6 +572,43 @@ def pfJ(nlm, Lmax=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# state ingest: a2 / a4 / a6 -> nlm (src/moments.f90:68-92)
+# ---------------------------------------------------------------------------------------------
+# affine maps extracted from include/a{2,4,6}_to_nlm__body.f90 by tools/make_ingest_tables.py (the a4 map composed
+# with a4_to_mat, src/mandel.f90:52-66); pinned by tests/golden (numeric interpretation of the same text).
+
+_ING = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "specfab_b200", "data", "ingest_l6.npz")
+_ing_cache = {}
+
+
+def _ai_to_nlm(tag, A, rank, nrow):
+    if not _ing_cache:
+        _ing_cache.update(np.load(_ING))
+    A = np.asarray(A, dtype=np.float64)
+    if A.shape != (3,) * rank:
+        raise ValueError("expected a tensor of shape %s" % ((3,) * rank,))
+    a = A.reshape(-1, order="F")
+    out = np.array(_ing_cache[tag + "_c0"], dtype=np.complex128)
+    np.add.at(out, _ing_cache[tag + "_row"], _ing_cache[tag + "_c"] * a[_ing_cache[tag + "_flat"]])
+    return out
+
+
+def a2_to_nlm(a2_):
+    """src/moments.f90:68-74 -> nlm(1:6)"""
+    return _ai_to_nlm("a2", a2_, 2, 6)
+
+
+def a4_to_nlm(a4_):
+    """src/moments.f90:76-84 -> nlm(1:15)"""
+    return _ai_to_nlm("a4", a4_, 4, 15)
+
+
+def a6_to_nlm(a6_):
+    """src/moments.f90:86-92 -> nlm(1:28)"""
+    return _ai_to_nlm("a6", a6_, 6, 28)
+
+
+# ---------------------------------------------------------------------------------------------
 # frames.f90
 # ---------------------------------------------------------------------------------------------
 

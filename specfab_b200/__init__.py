@@ -21,7 +21,7 @@ from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, Sp
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
-           "a6", "a6_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
+           "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
 
 _state = {"L": None, "n": None}
@@ -378,6 +378,41 @@ def pfJ_arr(nlm, Lmax=None):
     out = np.empty(N, dtype=np.float64)
     _lib.check(_lib.load().sfb_pfJ_arr(x.ctypes.data, N, N, Lmax, out.ctypes.data))
     return out
+
+
+def _ai_to_nlm_arr(rank, a):
+    x = _farr(a, np.float64, (3,) * rank)
+    N = x.shape[0]
+    out = np.empty((N, (rank + 1) * (rank + 2) // 2), dtype=np.complex128, order="F")
+    _lib.check(_lib.load().sfb_ai_to_nlm_arr(rank, x.ctypes.data, N, out.ctypes.data))
+    return out
+
+
+def a2_to_nlm_arr(a2_):
+    """a2 (N,3,3) -> nlm (N,6)                 reference per node: src/specfabpy.f90:619-627"""
+    return _ai_to_nlm_arr(2, a2_)
+
+
+def a4_to_nlm_arr(a4_):
+    """a4 (N,3,3,3,3) -> nlm (N,15)            reference per node: src/specfabpy.f90:629-637"""
+    return _ai_to_nlm_arr(4, a4_)
+
+
+def a6_to_nlm_arr(a6_):
+    """a6 (N,3,3,3,3,3,3) -> nlm (N,28)        reference per node: src/specfabpy.f90:639-647"""
+    return _ai_to_nlm_arr(6, a6_)
+
+
+def a2_to_nlm(a2_):
+    return np.ascontiguousarray(a2_to_nlm_arr(np.asarray(a2_)[None])[0])
+
+
+def a4_to_nlm(a4_):
+    return np.ascontiguousarray(a4_to_nlm_arr(np.asarray(a4_)[None])[0])
+
+
+def a6_to_nlm(a6_):
+    return np.ascontiguousarray(a6_to_nlm_arr(np.asarray(a6_)[None])[0])
 
 
 def eig_arr(nlm):

@@ -131,6 +131,7 @@ def generate(Ls):
     _write_if_changed(os.path.join(GEN, "tables.inc"), emit_tables.emit())
     _write_if_changed(os.path.join(GEN, "orth_tables.inc"), emit_tables.emit_orthotropic())
     _write_if_changed(os.path.join(GEN, "moments_hi.inc"), emit_tables.emit_moments_hi())
+    _write_if_changed(os.path.join(GEN, "ingest.inc"), emit_tables.emit_ingest())
     with open(os.path.join(GEN, "meta.json"), "w") as f:
         json.dump(metas, f, indent=1)
     return units, metas
@@ -144,7 +145,7 @@ def _deps_hash(src):
         tag = os.path.basename(src)[5:-3]
         files.append(os.path.join(GEN, "apply_%s.inc" % tag))
     else:
-        files += [os.path.join(GEN, "registry.inc"), os.path.join(GEN, "tables.inc"), os.path.join(GEN, "orth_tables.inc"), os.path.join(GEN, "moments_hi.inc")]
+        files += [os.path.join(GEN, "registry.inc"), os.path.join(GEN, "tables.inc"), os.path.join(GEN, "orth_tables.inc"), os.path.join(GEN, "moments_hi.inc"), os.path.join(GEN, "ingest.inc")]
     for f in files:
         h.update(open(f, "rb").read())
     h.update(" ".join(CFLAGS + ARCH).encode())

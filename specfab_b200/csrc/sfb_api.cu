@@ -33,6 +33,7 @@ cudaError_t sfb_launch_mexport_reduced(int mode, int L, const double* a33, const
                                        double* Mii, cudaStream_t st);
 cudaError_t sfb_launch_reduce_dense(const double* M, int is_complex, int L, long long N, long long ldi, double* Mrr, double* Mri,
                                     double* Mir, double* Mii, cudaStream_t st);
+cudaError_t sfb_launch_ingest(int rank, const double* A, long long N, long long ld, double2* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2* q2, long long ld2, const double2* q3, long long ld3,
                                 long long N, const double* e1, const double* e2, const double* e3, long long lde,
                                 const double* Eij_grain, int n_grain, double* Eij, long long ldo, cudaStream_t st);
@@ -508,6 +509,29 @@ int sfb_pfJ_arr(const double* nlm, int64_t N, int64_t ld, int Lmax, double* J) {
     CK(out.alloc((size_t)N * 8));
     if ((rc = sfb_pfJ_arr_dev(in.as<double>(), N, N, Lmax, out.as<double>(), nullptr))) return rc;
     CK(cudaMemcpy(J, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_ai_to_nlm_arr_dev(int rank, const double* a, int64_t N, int64_t ld, double* nlm, int64_t ld_nlm, void* stream) {
+    if (rank != 2 && rank != 4 && rank != 6) return fail(SFB_EINVAL, "rank must be 2, 4 or 6");
+    if (N < 0 || ld < N || ld_nlm < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    if (N == 0) return SFB_OK;
+    if (!a || !nlm) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_ingest(rank, a, N, ld, reinterpret_cast<double2*>(nlm), ld_nlm, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_ai_to_nlm_arr(int rank, const double* a, int64_t N, double* nlm) {
+    if (rank != 2 && rank != 4 && rank != 6) return fail(SFB_EINVAL, "rank must be 2, 4 or 6");
+    if (N < 0) return fail(SFB_EINVAL, "N < 0");
+    if (N == 0) return SFB_OK;
+    if (!a || !nlm) return fail(SFB_EINVAL, "null array");
+    const int ne = rank == 2 ? 9 : (rank == 4 ? 81 : 729), nrow = (rank + 1) * (rank + 2) / 2;
+    DevTmp di, dout;
+    CK(di.alloc((size_t)N * ne * 8));
+    CK(cudaMemcpy(di.p, a, (size_t)N * ne * 8, cudaMemcpyHostToDevice));
+    CK(dout.alloc((size_t)N * nrow * 16));
+    int rc = sfb_ai_to_nlm_arr_dev(rank, di.as<double>(), N, N, dout.as<double>(), N, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(nlm, dout.p, (size_t)N * nrow * 16, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }
 int sfb_Eij_orthotropic_arr_dev(const double* nlm_1, int64_t ld1, const double* nlm_2, int64_t ld2, const double* nlm_3, int64_t ld3,

@@ -8,6 +8,7 @@
 #include <cmath>
 
 #include "sfb_moments_hi.cuh"
+#include "gen/ingest.inc"
 
 namespace {
 
@@ -216,6 +217,35 @@ __global__ void __launch_bounds__(128) pfj_kernel(const double2* __restrict__ nl
     J[p] = 4 * 3.141592653589793 * acc;
 }
 
+// ---- state ingest a2 / a4 / a6 -> nlm(1:6 / 1:15 / 1:28)  (src/moments.f90:68-92): affine map of the tensor entries,
+// A (N, 3^k) Fortran order, table rows sorted so each output row is one running sum
+template <int TAG>
+__global__ void __launch_bounds__(128) ingest_kernel(const double* __restrict__ A, long long N, long long ld,
+                                                     double2* __restrict__ out, long long ldo) {
+    // the tables are __device__ symbols: they must be named in device code (a host-side address would be the shadow)
+    const short* row = TAG == 0 ? kIngRow_0 : (TAG == 1 ? kIngRow_1 : kIngRow_2);
+    const short* flat = TAG == 0 ? kIngFlat_0 : (TAG == 1 ? kIngFlat_1 : kIngFlat_2);
+    const double* cr = TAG == 0 ? kIngRe_0 : (TAG == 1 ? kIngRe_1 : kIngRe_2);
+    const double* ci = TAG == 0 ? kIngIm_0 : (TAG == 1 ? kIngIm_1 : kIngIm_2);
+    const double* c0r = TAG == 0 ? kIngC0Re_0 : (TAG == 1 ? kIngC0Re_1 : kIngC0Re_2);
+    const double* c0i = TAG == 0 ? kIngC0Im_0 : (TAG == 1 ? kIngC0Im_1 : kIngC0Im_2);
+    constexpr int nnz = TAG == 0 ? SFB_ING_NNZ_0 : (TAG == 1 ? SFB_ING_NNZ_1 : SFB_ING_NNZ_2);
+    constexpr int nrow = TAG == 0 ? SFB_ING_NROW_0 : (TAG == 1 ? SFB_ING_NROW_1 : SFB_ING_NROW_2);
+    const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (p >= N) return;
+    int t = 0;
+    for (int r = 0; r < nrow; ++r) {
+        double2 acc = make_double2(c0r[r], c0i[r]);
+        while (t < nnz && row[t] == r) {
+            const double a = A[(long long)flat[t] * ld + p];
+            acc.x = fma(cr[t], a, acc.x);
+            acc.y = fma(ci[t], a, acc.y);
+            ++t;
+        }
+        out[(long long)r * ldo + p] = acc;
+    }
+}
+
 cudaError_t ensure_iso(cudaStream_t st) {
     static bool done[64] = {};
     int dev = 0;
@@ -252,5 +282,13 @@ cudaError_t sfb_launch_caffe(const double2* nlm, long long N, long long ld, cons
 }
 cudaError_t sfb_launch_pfj(const double2* nlm, long long N, long long ld, int Lmax, double* J, cudaStream_t st) {
     if (N > 0) pfj_kernel<<<nblk(N, 128), 128, 0, st>>>(nlm, N, ld, Lmax, J);
+    return cudaGetLastError();
+}
+cudaError_t sfb_launch_ingest(int rank, const double* A, long long N, long long ld, double2* out, long long ldo, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const unsigned nb = nblk(N, 128);
+    if (rank == 2) ingest_kernel<0><<<nb, 128, 0, st>>>(A, N, ld, out, ldo);
+    else if (rank == 4) ingest_kernel<1><<<nb, 128, 0, st>>>(A, N, ld, out, ldo);
+    else ingest_kernel<2><<<nb, 128, 0, st>>>(A, N, ld, out, ldo);
     return cudaGetLastError();
 }

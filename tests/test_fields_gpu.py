@@ -361,3 +361,20 @@ def test_pfJ_parity():
         assert np.abs(J / ref - 1).max() < 1e-14
     with pytest.raises((sf.SpecfabB200Error, ValueError)):
         sf.pfJ_arr(x, 10)
+
+
+@pytest.mark.parametrize("rank", [2, 4, 6])
+def test_state_ingest_parity(rank):
+    """a2/a4/a6 -> nlm (src/moments.f90:68-92) on arbitrary tensors and as the inverse of a2/a4/a6"""
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    rng = np.random.default_rng(90 + rank)
+    A = rng.standard_normal((50,) + (3,) * rank)
+    got = getattr(sf, "a%d_to_nlm_arr" % rank)(A)
+    ref = np.array([getattr(orc, "a%d_to_nlm" % rank)(a) for a in A])
+    assert got.shape == ref.shape and relerr_nodes(got, ref).max() < 1e-14
+    x = random_states(L, 20, 95, True, decay=0.4)
+    back = getattr(sf, "a%d_to_nlm_arr" % rank)(getattr(sf, "a%d_arr" % rank)(x))
+    assert np.abs(back - x[:, :back.shape[1]]).max() < 1e-7
+    assert np.array_equal(getattr(sf, "a%d_to_nlm" % rank)(A[3]), got[3])

@@ -208,3 +208,29 @@ def test_high_order_contractions_and_closures():
     S = np.diag([.5, .5, -1.])
     assert abs(o.ev_D4(iso, S) - 1) < 1e-6 and abs(o.E_CAFFE(iso, S, 0.1, 10, 1) - 1) < 1e-12
     assert abs(o.E_CAFFE(iso, S, 0.1, 10, 3) - 1) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["a2", "a4", "a6"])
+def test_state_ingest_maps(tag):
+    """src/moments.f90:68-92: extracted affine maps against the numeric interpretation of the reference bodies, on
+    arbitrary (non-symmetric) tensors so that every index the bodies read is pinned"""
+    f = getattr(o, tag + "_to_nlm")
+    for c in range(G["ingest_" + tag].shape[0]):
+        r = f(G["ingest_" + tag][c])
+        ref = G["ingest_" + tag + "_nlm"][c]
+        assert np.abs(r - ref).max() < 5e-15 * np.abs(ref).max()
+
+
+def test_state_ingest_round_trip():
+    """SURVEY 8c pin (7): nlm - a4_to_nlm(a4(nlm)) is small (float32-constant accuracy), tests/ai-to-nlm/ai-to-nlm.py:95"""
+    o.init(8)
+    rng = np.random.default_rng(4)
+    x = np.zeros(45, complex); x[0] = 1 / np.sqrt(4 * np.pi)
+    lm = [(l, m) for l in range(0, 9, 2) for m in range(-l, l + 1)]
+    idx = {k: j for j, k in enumerate(lm)}
+    x[1:] = 0.03 * (rng.standard_normal(44) + 1j * rng.standard_normal(44))
+    for (l, m), j in idx.items():
+        x[j] = x[j].real if m == 0 else ((-1) ** abs(m) * np.conj(x[idx[(l, -m)]]) if m < 0 else x[j])
+    assert np.abs(o.a2_to_nlm(o.a2(x)) - x[:6]).max() < 1e-7
+    assert np.abs(o.a4_to_nlm(o.a4(x)) - x[:15]).max() < 1e-7
+    assert np.abs(o.a6_to_nlm(o.a6(x)) - x[:28]).max() < 1e-7

@@ -178,7 +178,13 @@ def _f_aimag(a):
     raise TypeError
 
 
-INTRINSICS = {"sqrt": _f_sqrt, "real": _f_real, "aimag": _f_aimag}
+def _f_conjg(a):
+    if a.k[0] != "c":
+        raise TypeError("conjg of a non-complex value")
+    return V(a.k, a.v.conjugate())
+
+
+INTRINSICS = {"sqrt": _f_sqrt, "real": _f_real, "aimag": _f_aimag, "conjg": _f_conjg}
 
 _TOK = re.compile(r"\s*(?:(\d+\.\d*(?:[dDeE][-+]?\d+)?|\.\d+(?:[dDeE][-+]?\d+)?|\d+[dDeE][-+]?\d+|\d+)|([A-Za-z_][A-Za-z_0-9]*)|(\*\*|[-+*/(),=]))")
 

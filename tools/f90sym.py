@@ -103,13 +103,20 @@ class RealOf(Poly):
         super().__init__(p.t)
 
 
+def _s_conjg(a):
+    """conjugate of a polynomial in REAL variables: conjugate the coefficients"""
+    if isinstance(a, Poly):
+        return Poly({k: complex(c).conjugate() for k, c in a.t.items()})
+    return fe._f_conjg(a)
+
+
 def install():
     fe.binop = sbinop
     fe.neg = sneg
-    fe.INTRINSICS = dict(fe.INTRINSICS, real=_s_real)
+    fe.INTRINSICS = dict(fe.INTRINSICS, real=_s_real, conjg=_s_conjg)
 
 
 def uninstall():
     fe.binop = _orig_binop
     fe.neg = _orig_neg
-    fe.INTRINSICS = dict(fe.INTRINSICS, real=fe._f_real)
+    fe.INTRINSICS = dict(fe.INTRINSICS, real=fe._f_real, conjg=fe._f_conjg)

@@ -187,6 +187,31 @@ for tag, fn, rank in (("c6", "ev_c6__body.f90", 6), ("c8", "ev_c8__body.f90", 8)
             res[(c,) + tuple(i - 1 for i in key)] = val.v * env["k"].v / c0      # ev = ev * k/f_ev_c0(n00)  (:226,:235)
     out["hi_" + tag] = res
 
+# ---- state ingest a2/a4/a6 -> nlm (affine maps, real(4) constants, conjg rows): numeric interpretation ----
+# arbitrary (non-symmetric) arrays: the bodies read specific entries, which pins the index handling
+import itertools
+NI = 2
+SQ2 = float(np.sqrt(2.0))
+for tag, fn, rank, nrow in (("a2", "a2_to_nlm__body.f90", 2, 6), ("a4", "a4_to_nlm__body.f90", 4, 15), ("a6", "a6_to_nlm__body.f90", 6, 28)):
+    A = rng.standard_normal((NI,) + (3,) * rank)
+    res = np.zeros((NI, nrow), dtype=np.complex128)
+    for c in range(NI):
+        env = {"Pi": PI}
+        if tag == "a4":
+            pairs = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
+            man = {}
+            for i in range(6):          # a4_to_mat, src/mandel.f90:52-66
+                for j in range(6):
+                    f = 2.0 if (i >= 3 and j >= 3) else (SQ2 if (i >= 3 or j >= 3) else 1.0)
+                    man[(i + 1, j + 1)] = V("r8", f * A[c][pairs[i] + pairs[j]])
+            env["a4Mandel"] = man
+        else:
+            env[tag] = {tuple(i + 1 for i in idx): V("r8", A[c][idx]) for idx in itertools.product(range(3), repeat=rank)}
+        run_body(rd("include", fn), env, {"nlm": "c8"})
+        res[c] = [env["nlm"][k + 1].v for k in range(nrow)]
+    out["ingest_" + tag] = A
+    out["ingest_" + tag + "_nlm"] = res
+
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "refbodies.npz")
 np.savez_compressed(dst, **out)
 print("wrote", os.path.normpath(dst), {k: v.shape for k, v in out.items()})
