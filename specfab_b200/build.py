@@ -35,13 +35,18 @@ EXTRA = {
     #   R = -1: persistent four-lane kernel (streaming TMA refill); R = -2: table-driven loop kernel (+rN roles, +chN rows/chunk)
     (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 2, 16, 7, "imm", False), (12, 2, 16, 6, "imm", False), (13, 2, 16, 5, "imm", False), (14, 2, 32, 3, "imm", False),
-             (15, 3, 16, 7, "imm", False), (16, 2, 16, 7, "imm+c6", False)],
+             (15, 3, 16, 7, "imm", False), (16, 2, 16, 7, "imm+c6", False),
+             (25, -3, 32, 7, "imm", False), (26, -3, 32, 6, "imm", False), (27, -3, 32, 5, "imm", False)],
     (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
-             (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False)],
-    (12, 0): [(2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
+             (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False),
+             (25, -3, 32, 4, "imm", False), (26, -3, 32, 3, "imm", False), (27, -3, 32, 5, "imm", False)],
+    (4, 0): [(25, -3, 32, 8, "imm", False)], (4, 1): [(25, -3, 32, 8, "imm", False)],
+    (6, 0): [(25, -3, 32, 8, "imm", False)], (6, 1): [(25, -3, 32, 6, "imm", False)],
+    (10, 0): [(25, -3, 32, 5, "imm", False)], (10, 1): [(25, -3, 32, 3, "imm", False)],
+    (12, 0): [(25, -3, 32, 4, "imm", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
               (1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
-    (12, 1): [(2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
+    (12, 1): [(25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
               (10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
     (20, 0): [(2, 5, 16, 3, "imm", False), (3, 4, 16, 3, "imm", False), (4, 7, 16, 2, "imm", False),
               (1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],
@@ -52,16 +57,31 @@ EXTRA = {
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
 #   DDRX kernels up to L = 8 prefer four lanes per node;  L >= 12 with DDRX and every L >= 14: the table-driven loop kernel
 #   (straight-line code of 150 KB .. 1 MB per stage is instruction-fetch bound, profiles/r01_notes.md).
+#   R = -3: reduced one-lane kernel (real-ODF symmetry detected per tile, in-kernel two-lane fallback for general complex
+#   states): half the arithmetic and shared memory per node; 1.2-1.9x the node rate wherever the straight-line form is used.
 TUNE = {
-    (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
-    (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
-    (8, 0): (1, 16, 6, "imm", False), (8, 1): (0, 64, 2, "imm", False),
-    (10, 0): (0, 16, 4, "imm+w", True), (10, 1): (-2, 32, 2, "imm+ch2+r4", False),
-    (12, 0): (0, 16, 4, "imm+w", True), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
+    (4, 0): (-3, 32, 8, "imm", False), (4, 1): (-3, 32, 8, "imm", False),
+    (6, 0): (-3, 32, 8, "imm", False), (6, 1): (-3, 32, 6, "imm", False),
+    (8, 0): (-3, 32, 7, "imm", False), (8, 1): (0, 64, 2, "imm", False),
+    (10, 0): (-3, 32, 5, "imm", False), (10, 1): (-2, 32, 2, "imm+ch2+r4", False),
+    (12, 0): (-3, 32, 4, "imm", False), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
     (14, 0): (-2, 16, 4, "imm+ch2+r4", False), (14, 1): (-2, 16, 3, "imm+ch2+r4", False),
     (16, 0): (-2, 16, 4, "imm+ch2+r6", False), (16, 1): (-2, 16, 3, "imm+ch2+r6", False),
     (18, 0): (-2, 16, 3, "imm+ch2+r6", False), (18, 1): (-2, 16, 2, "imm+ch2+r6", False),
     (20, 0): (-2, 16, 3, "imm+ch2+r6", False), (20, 1): (-2, 16, 2, "imm+ch2+r6", False),
+}
+
+
+# scheme-specific default: variant 100 (when present) replaces variant 0 for multi-stage (RK4) steps -- with DDRX the
+# classical RK4 keeps three state buffers, which favours the reduced kernel's halved footprint
+TUNE_RK = {
+    (8, 1): (-3, 32, 4, "imm", False), (10, 1): (-3, 32, 3, "imm", False),
+}
+# the previous full-form defaults stay selectable (variant 40) for comparisons
+FULL_DEFAULT = {
+    (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
+    (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
+    (8, 0): (1, 16, 6, "imm", False), (10, 0): (0, 16, 4, "imm+w", True), (12, 0): (0, 16, 4, "imm+w", True),
 }
 
 
@@ -81,7 +101,13 @@ def generate(Ls):
     for L in Ls:
         for dd in (0, 1):
             R, TN, MINB, cm0, sy0 = TUNE[(L, dd)]
-            variants = [(0, R, TN, MINB, cm0, sy0)] + (EXTRA.get((L, dd), []) if os.environ.get("SFB_EXTRA_VARIANTS", "1") == "1" else [])
+            variants = [(0, R, TN, MINB, cm0, sy0)]
+            if (L, dd) in TUNE_RK:
+                variants.append((100,) + TUNE_RK[(L, dd)])
+            if os.environ.get("SFB_EXTRA_VARIANTS", "1") == "1":
+                if (L, dd) in FULL_DEFAULT:
+                    variants.append((40,) + FULL_DEFAULT[(L, dd)])
+                variants += [v for v in EXTRA.get((L, dd), []) if v[1:] != variants[0][1:]]
             for (vid, R, TN, MINB, cmode, sync) in variants:
                 tag = "L%d_%s" % (L, "ddrx" if dd else "lrot") + ("_v%d" % vid if vid else "")
                 # const_mode string: "imm" | "cbank", optional flags "+w" (register window), "+cN" (>= N DFMA
@@ -100,6 +126,15 @@ def generate(Ls):
                     skeleton = "sfb_step_kernel.cuh"
                     R = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])     # warp roles per node group
                     meta["R"] = R
+                elif R == -3:      # reduced one-lane kernel for real-ODF states (+ in-kernel two-lane fallback, tiles of 16)
+                    body, tab, meta = emit_step.emit(L, dd, 1, TN, cm, False, mc, gd, reduced=True)
+                    fbody, _, fmeta = emit_step.emit(L, dd, 1, 16, cm, False, mc, gd)
+                    _write_if_changed(os.path.join(GEN, "apply_%s_full.inc" % tag), fbody)
+                    tab = ('#define SFB_REDUCED 1\n#define SFB_TNR %d\n#define SFB_APPLY_INC_R "gen/apply_%s.inc"\n' % (TN, tag)) + tab
+                    skeleton = "sfb_step_kernel.cuh"
+                    meta["dfma_node_full"] = fmeta["dfma_node"]
+                    meta["reduced"] = 1
+                    R_cu, TN_cu, inc_cu = 1, 16, "gen/apply_%s_full.inc" % tag
                 elif R == -1:      # persistent, lock-stepped, streaming refill (four lanes per node)
                     body, tab, meta = emit_step.emit4(L, dd, TN, cm, True, window, mc, gd)
                     skeleton = "sfb_step_kernel5.cuh"
@@ -111,9 +146,13 @@ def generate(Ls):
                     body, tab, meta = emit_step.emit(L, dd, R, TN, cm, sync, mc, gd)
                     skeleton = "sfb_step_kernel.cuh"
                 _write_if_changed(os.path.join(GEN, "apply_%s.inc" % tag), body)
+                if meta.get("reduced"):
+                    r_cu, tn_cu, inc = R_cu, TN_cu, inc_cu
+                else:
+                    r_cu, tn_cu, inc = R, TN, "gen/apply_%s.inc" % tag
                 cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_R %d\n#define SFB_TN %d\n#define SFB_MINB %d\n'
-                      '#define SFB_NAME sfb_launch_step_%s\n#define SFB_APPLY_INC "gen/apply_%s.inc"\n%s'
-                      '#include "%s"\n' % (L, dd, R, TN, MINB, tag, tag, tab, skeleton))
+                      '#define SFB_NAME sfb_launch_step_%s\n#define SFB_APPLY_INC "%s"\n%s'
+                      '#include "%s"\n' % (L, dd, r_cu, tn_cu, MINB, tag, inc, tab, skeleton))
                 path = os.path.join(GEN, "step_%s.cu" % tag)
                 _write_if_changed(path, cu)
                 units.append(path)
@@ -144,6 +183,8 @@ def _deps_hash(src):
     if "step_" in os.path.basename(src):
         tag = os.path.basename(src)[5:-3]
         files.append(os.path.join(GEN, "apply_%s.inc" % tag))
+        if os.path.exists(os.path.join(GEN, "apply_%s_full.inc" % tag)):
+            files.append(os.path.join(GEN, "apply_%s_full.inc" % tag))
     else:
         files += [os.path.join(GEN, "registry.inc"), os.path.join(GEN, "tables.inc"), os.path.join(GEN, "orth_tables.inc"), os.path.join(GEN, "moments_hi.inc"), os.path.join(GEN, "ingest.inc")]
     for f in files:

@@ -80,14 +80,16 @@ const double kNu[9] = {1.9879322126397958, 3.0011508426238862, 5.749806992135238
                        19.9467342880730136};
 
 int g_variant = 0;   // tuning knob (sfb_set_variant); falls back to variant 0 when absent
-const SfbStepEntry* find_step(int L, int ddrx) {
-    const SfbStepEntry* def = nullptr;
+// variant 0 is the default; variant 100, when compiled, is the default for multi-stage (RK4) steps (build.py TUNE_RK)
+const SfbStepEntry* find_step(int L, int ddrx, int nstage) {
+    const SfbStepEntry *def = nullptr, *rk = nullptr;
     for (const auto& e : kStepRegistry)
         if (e.L == L && e.ddrx == ddrx) {
-            if (e.variant == g_variant) return &e;
+            if (g_variant != 0 && e.variant == g_variant) return &e;
             if (e.variant == 0) def = &e;
+            if (e.variant == 100) rk = &e;
         }
-    return def;
+    return (g_variant == 0 && nstage > 1 && rk) ? rk : def;
 }
 
 // ---- host-pointer staging: per-thread ring of device chunk buffers -------------------------
@@ -121,7 +123,7 @@ const char* sfb_last_error(void) { return t_err.empty() ? g.err.c_str() : t_err.
 int sfb_init(int L) {
     std::lock_guard<std::mutex> lk(g.mu);
     if (L % 2 != 0 || L < 4 || L > SFB_MAXL) return fail(SFB_EINVAL, "sfb_init: L must be even, 4 <= L <= 20");
-    if (!find_step(L, 0) || !find_step(L, 1)) return fail(SFB_ENOTBUILT, "sfb_init: kernels for this L were not compiled");
+    if (!find_step(L, 0, 1) || !find_step(L, 1, 1)) return fail(SFB_ENOTBUILT, "sfb_init: kernels for this L were not compiled");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -193,7 +195,7 @@ int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t l
     if (((uintptr_t)nlm_in & 15) || ((uintptr_t)nlm_out & 15)) return fail(SFB_EINVAL, "nlm arrays must be 16-byte aligned");
     const int ddrx = (o->terms & SFB_DDRX) ? 1 : 0;
     if (ddrx && tau && ld_t < N) return fail(SFB_EINVAL, "ld_t < N");
-    const SfbStepEntry* ent = find_step(g.L, ddrx);
+    const SfbStepEntry* ent = find_step(g.L, ddrx, o->scheme == SFB_RK4 ? 4 : 1);
     if (!ent) return fail(SFB_ENOTBUILT, "step kernel for this L not compiled");
     SfbStepParams P;
     P.nlm_in = reinterpret_cast<const double2*>(nlm_in);

@@ -102,7 +102,11 @@ __device__ __forceinline__ void load_tau(const ForcSrc& S, double T[3][3]) {
     }
 }
 
+// TNS: node stride of the forcing / scalar arrays; WITHB: also fill the mirrored block of lane set B
+// (the one-lane reduced kernel, sfb_step_kernel_r.cuh, needs set A only)
+template <int TNS = kTN, bool WITHB = true>
 __device__ void prep_lrot(const SfbStepParams& P, const ForcSrc& S, long long node, int t, double2* forc, double* scal) {
+    constexpr int kTN = TNS;                   // shadows the tile constant inside this function
     double D[3][3], W[3][3];
     load_sym_skew(S, D, W);
     double2* fA = forc + t;                    // lane set A block: entry e at fA[e*kTN]
@@ -129,11 +133,11 @@ __device__ void prep_lrot(const SfbStepParams& P, const ForcSrc& S, long long no
         for (int i = 0; i < 3; ++i) qo[i] = make_double2(0.0, 0.0);
     }
 #pragma unroll
-    for (int d = -2; d <= 2; ++d) { fA[(d + 2) * kTN] = qe[d + 2]; fB[(d + 2) * kTN] = qe[-d + 2]; }
+    for (int d = -2; d <= 2; ++d) { fA[(d + 2) * kTN] = qe[d + 2]; if (WITHB) fB[(d + 2) * kTN] = qe[-d + 2]; }
 #pragma unroll
     for (int d = -1; d <= 1; ++d) {
-        fA[(5 + d + 1) * kTN] = make_double2(-qo[d + 1].y, qo[d + 1].x);        //  i*qo[d]
-        fB[(5 + d + 1) * kTN] = make_double2(qo[-d + 1].y, -qo[-d + 1].x);      // -i*qo[-d]
+        fA[(5 + d + 1) * kTN] = make_double2(-qo[d + 1].y, qo[d + 1].x);                   //  i*qo[d]
+        if (WITHB) fB[(5 + d + 1) * kTN] = make_double2(qo[-d + 1].y, -qo[-d + 1].x);      // -i*qo[-d]
     }
     // M_REG: -nu*||D||_F * regdiag   src/dynamics.f90:516-517
     double fro = 0.0;
@@ -147,7 +151,9 @@ __device__ void prep_lrot(const SfbStepParams& P, const ForcSrc& S, long long no
 }
 
 #if SFB_DDRX
+template <int TNS = kTN, bool WITHB = true>
 __device__ void prep_ddrx_g(const SfbStepParams& P, const ForcSrc& S, long long node, int t, double2* forc, double* scal) {
+    constexpr int kTN = TNS;
     double2* fA = forc + t;
     double2* fB = forc + kNF * kTN + t;
     const double g0 = P.gamma0_arr ? P.gamma0_arr[node] : P.gamma0;
@@ -168,10 +174,12 @@ __device__ void prep_ddrx_g(const SfbStepParams& P, const ForcSrc& S, long long 
 #pragma unroll
     for (int k = 0; k < 15; ++k) g[k] = make_double2(sc * g[k].x, sc * g[k].y);
 #pragma unroll
-    for (int k = 0; k < 15; ++k) { fA[(8 + k) * kTN] = g[k]; fB[(8 + k) * kTN] = g[cat_mirror(k)]; }
+    for (int k = 0; k < 15; ++k) { fA[(8 + k) * kTN] = g[k]; if (WITHB) fB[(8 + k) * kTN] = g[cat_mirror(k)]; }
 }
 
+template <int TNS = kTN>
 __device__ void prep_ddrx_d(const ForcSrc& S, int t, double* scal) {
+    constexpr int kTN = TNS;
     // <D> ingredients, src/dynamics.f90:415-417
     double T[3][3];
     load_tau(S, T);

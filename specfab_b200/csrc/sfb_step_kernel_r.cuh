@@ -1,0 +1,253 @@
+// Reduced-form fused step kernel: ONE lane per node for states with the real-ODF symmetry
+//     n_l^{-m} = (-1)^m conj(n_l^m),  Im n_l^0 = 0            (every physical ODF; src/reducedform.f90:160-170).
+// M_LROT, M_DDRX_src and the diagonal terms commute with this mirror (exact mirror symmetry of the Gaunt tables,
+// codegen/operators.py), so the rows m < 0 of the new state are the mirror of the rows m >= 0 and only the
+// latter are computed: half the DFMAs, half the shared memory and half of the state read of the full kernel.
+// The mirror rows are still WRITTEN (the output is a full nlm array, like the reference's).
+//
+// The symmetry is verified per tile against the rows m < 0 of the input (read once from global, never staged),
+// to round-off: every component of n_l^{-m} - (-1)^m conj(n_l^m) and of Im n_l^0 must be within kSymTol * |n_0^0|
+// (2^-46 ~ 1.4e-14: what a chain of FP64 steps of the full algorithm -- or of the reference -- leaves behind;
+// two orders below the 1e-12 per-step parity bar).  The reduced path then works from the rows m >= 0 and writes an
+// exactly symmetric state.  A tile that fails the test -- general complex vectors are legal input for the
+// reference operators -- is handed to full_tile() (sfb_step_kernel.cuh), the unreduced two-lane algorithm, 16
+// nodes at a time inside the same CTA and the same shared-memory footprint.  Included at the end of sfb_step_kernel.cuh
+// when SFB_REDUCED is defined; SFB_TNR = nodes per CTA here (= 2 * SFB_TN), SFB_APPLY_INC_R = generated body.
+#pragma once
+
+namespace {
+
+constexpr int kTNR = SFB_TNR;
+constexpr double kSymTol = 0x1p-46;
+constexpr int kNRowR = (kL / 2 + 1) * (kL / 2 + 1);       // rows (l, m >= 0)
+static_assert(kTNR == 32 && kTN == 16 && kR == 1 && kThreads == 32, "reduced kernel: one warp, 32 nodes, fallback tiles of 16");
+
+struct CtxR {
+    const double2* yp;                // stage input, rows pslot(l, m) * kTNR
+    const double2* fz;                // forcing block (lane set A's)
+    double2* op;                      // next-stage buffer
+    double2* ap;                      // RK accumulator buffer (classical RK4)
+    double2* gout;                    // global output, offset by node
+    const double2* gin;
+    long long ld_out, ld_in;
+    double c0, lam, rm;
+    double as, bs;
+    bool first, last, valid, ld_n0, ld_acc;
+};
+
+template <int l, int mu>
+__device__ __forceinline__ double2 n0_load_r(const CtxR& c) {
+    double2 v = make_double2(0.0, 0.0);
+    if (c.ld_n0) v = c.gin[(long long)(hrow(l) + mu) * c.ld_in];
+    return v;
+}
+template <int l, int mu>
+__device__ __forceinline__ double2 acc_load_r(const CtxR& c) {
+    double2 v = make_double2(0.0, 0.0);
+#if !SFB_HORNER
+    if (c.ld_acc) v = c.ap[pslot(l, mu) * kTNR];
+#endif
+    return v;
+}
+template <int l, int mu>
+__device__ __forceinline__ void row_out_r(const CtxR& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
+    double d = fma(c.lam, -(double)(l * (l + 1)), c.c0);
+    d = fma(c.rm, c_reg.regdiag[l / 2], d);
+    kr = fma(d, zr, kr);
+    ki = fma(d, zi, ki);
+    if (mu == 0) { ki = 0.0; zi = 0.0; n0.y = 0.0; acc.y = 0.0; }     // n_l^0 of a real ODF is real: drop the round-off
+    constexpr int off = pslot(l, mu) * kTNR;
+    const double n0r = c.first ? zr : n0.x, n0i = c.first ? zi : n0.y;
+#if SFB_HORNER
+    const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
+    if (!c.last) c.op[off] = y;
+    const double2 res = y;
+#else
+    const double2 A = make_double2(fma(c.bs, kr, c.first ? zr : acc.x), fma(c.bs, ki, c.first ? zi : acc.y));
+    const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
+    if (!c.last) { c.op[off] = y; c.ap[off] = A; }
+    const double2 res = A;
+#endif
+    if (c.last && c.valid) {
+        c.gout[(long long)(hrow(l) + mu) * c.ld_out] = res;
+        if (mu != 0)      // mirror row: (-1)^mu conj
+            c.gout[(long long)(hrow(l) - mu) * c.ld_out] = (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y);
+    }
+}
+#define SFB_RROW_PRE(l, mu, q, r) const double2 q = n0_load_r<l, mu>(c), r = acc_load_r<l, mu>(c)
+#define SFB_RROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out_r<l, mu>(c, ar, ai, zr, zi, q, r)
+
+__device__ __forceinline__ void apply_reduced(const CtxR& c) {
+    const double2* __restrict__ yp = c.yp;
+    const double2* __restrict__ fz = c.fz;
+    const int role = 0;
+#include SFB_APPLY_INC_R
+}
+
+__global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nbuf = P.nstage == 1 ? 1 : (SFB_HORNER ? 2 : 3);
+    double2* bufs = reinterpret_cast<double2*>(smem_raw);
+    double2* forc = bufs + (size_t)nbuf * kNRowR * kTNR;
+    double* scal = reinterpret_cast<double*>(forc + kNF * kTNR);
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(scal + kNSc * kTNR);
+
+    const int t = threadIdx.x;                        // node within tile
+    const long long node0 = (long long)blockIdx.x * kTNR;
+    const int nvalid = (int)min((long long)kTNR, P.N - node0);
+    const bool valid = t < nvalid;
+
+    // ---- stage the rows m >= 0 of the tile (one bulk copy per row) into buffer 0
+    const uint32_t mb = smem_u32(mbar);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    {
+        const uint32_t bytes = (uint32_t)nvalid * 16u;
+        if (t == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes * (uint32_t)kNRowR) : "memory");
+        __syncwarp();
+        for (int r = t; r < kNRowR; r += 32) {
+            // reduced row r = (l/2)^2 + m
+            int h = 0;
+            while ((h + 1) * (h + 1) <= r) ++h;
+            const int l = 2 * h, m = r - h * h;
+            const uint32_t dst = smem_u32(bufs + (size_t)r * kTNR);
+            const double2* src = P.nlm_in + (long long)(hrow(l) + m) * P.ld_in + node0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+        }
+    }
+    // ---- meanwhile: per-node forcing (lane set A only)
+    if (valid) {
+        const ForcSrc S = global_src(P, node0 + t);
+        prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal);
+#if SFB_DDRX
+        prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
+        prep_ddrx_d<kTNR>(S, t, scal);
+#endif
+    }
+    {   // wait for the tile
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(mb) : "memory");
+        }
+    }
+    __syncwarp();
+
+    // ---- real-ODF symmetry of the input to round-off (NaNs fail the test and take the general path)
+    bool bad = false;
+    if (valid) {
+        const double2* gin = P.nlm_in + node0 + t;
+        const double tol = kSymTol * fabs(bufs[t].x);
+#pragma unroll 1
+        for (int l = 0; l <= kL; l += 2) {
+            bad |= !(fabs(bufs[(size_t)pslot(l, 0) * kTNR + t].y) <= tol);
+            for (int m = 1; m <= l; ++m) {
+                const double2 vp = bufs[(size_t)pslot(l, m) * kTNR + t];
+                const double2 vn = gin[(long long)(hrow(l) - m) * P.ld_in];
+                const double er = (m & 1) ? -vp.x : vp.x, ei = (m & 1) ? vp.y : -vp.y;
+                bad |= !(fabs(vn.x - er) <= tol && fabs(vn.y - ei) <= tol);
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+        if (t == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
+        __syncwarp();
+        full_tile(P, node0, smem_raw);
+        if (node0 + kTN < P.N) full_tile(P, node0 + kTN, smem_raw);
+        return;
+    }
+
+    CtxR c;
+    c.valid = valid;
+    c.fz = forc + t;
+    c.lam = scal[SC_LAM * kTNR + t];
+    c.rm = scal[SC_RM * kTNR + t];
+    c.c0 = 0.0;
+    c.ld_out = P.ld_out;
+    c.ld_in = P.ld_in;
+    c.gout = P.nlm_out + node0 + t;
+    c.gin = P.nlm_in + node0 + t;
+    c.ap = bufs + (size_t)(nbuf - 1) * kNRowR * kTNR + t;
+
+    for (int s = 0; s < P.nstage; ++s) {
+        const int ib = s & 1, ob = (s + 1) & 1;
+        c.yp = bufs + (size_t)ib * kNRowR * kTNR + t;
+        c.op = bufs + (size_t)ob * kNRowR * kTNR + t;
+        c.first = (s == 0);
+        c.last = (s == P.nstage - 1);
+        c.ld_n0 = !c.first && c.valid && (SFB_HORNER || !c.last);
+        c.ld_acc = !c.first;
+#if SFB_HORNER
+        c.as = (P.nstage == 1) ? P.dt : P.dt / (double)(4 - s);
+        c.bs = 0.0;
+#else
+        if (P.nstage == 1) { c.as = 0.0; c.bs = P.dt; }
+        else {
+            c.as = (s == 2) ? P.dt : 0.5 * P.dt;
+            c.bs = (s == 0 || s == 3) ? P.dt / 6 : P.dt / 3;
+        }
+#endif
+#if SFB_DDRX
+        if (valid) {   // <D>(current stage state)
+            const double2* y = c.yp;
+            double2 n2[3], n4[5];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) n2[m] = y[pslot(2, m) * kTNR];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[pslot(4, m) * kTNR] : make_double2(0.0, 0.0);
+            double tv[6], sv[6];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) { tv[p] = scal[(SC_TAUV + p) * kTNR + t]; sv[p] = scal[(SC_TSQV + p) * kTNR + t]; }
+            const double davg = sfb::ev_D2(y[0], n2, n4, tv, sv, scal[SC_NORM * kTNR + t]);
+            c.c0 = -(scal[SC_G0 * kTNR + t] * davg);
+        }
+#endif
+        apply_reduced(c);
+        // every lane reads and writes only its own node's column: no barrier between stages
+    }
+}
+
+}  // namespace
+
+extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
+    static bool attr_done[64] = {false};
+    const size_t fixed = (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16;
+    const size_t per_buf = (size_t)kNRowR * kTNR * 16;
+    const int nbuf_rk = SFB_HORNER ? 2 : 3;
+    const size_t smem_max = nbuf_rk * per_buf + fixed;
+    // the general-path fallback (full_tile, 16 nodes, both row planes, both forcing blocks) uses the same bytes
+    static_assert((size_t)kNRow * kTN == (size_t)kNRowR * kTNR && 2 * kNF * kTN == kNF * kTNR, "fallback must fit the reduced layout");
+    if (smem_max > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr_done[dev]) {
+        e = cudaFuncSetAttribute(step_kernel_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    SfbStepParams P = Pin;
+    P.n0_global = 1;
+    const int nbuf = P.nstage == 1 ? 1 : nbuf_rk;
+    const size_t smem = nbuf * per_buf + fixed;
+    {
+        static SfbRegConst last[64];
+        static bool have[64] = {false};
+        if (!have[dev] || memcmp(&last[dev], &reg, sizeof(SfbRegConst)) != 0) {
+            e = cudaMemcpyToSymbolAsync(c_reg, &reg, sizeof(SfbRegConst), 0, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            last[dev] = reg;
+            have[dev] = true;
+        }
+    }
+    if (P.N <= 0) return cudaSuccess;
+    const long long ntile = (P.N + kTNR - 1) / kTNR;
+    step_kernel_r<<<(unsigned)ntile, 32, smem, st>>>(P);
+    return cudaGetLastError();
+}

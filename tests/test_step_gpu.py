@@ -34,7 +34,7 @@ def built_L():
     return sorted({k["L"] for k in sf.build_info()["step_kernels"]})
 
 
-@pytest.mark.parametrize("L", [4, 6, 8, 12, 20])
+@pytest.mark.parametrize("L", [4, 6, 8, 10, 12, 20])
 @pytest.mark.parametrize("scheme", ["euler", "rk4"])
 @pytest.mark.parametrize("physical", [True, False])
 def test_step_lrot_reg(L, scheme, physical):
@@ -189,3 +189,47 @@ def test_large_field_linearity_property():
     sel = rng.choice(N, 16, replace=False)
     ref = oracle_steps(L, x1[sel], ug[sel], None, "rk4", 1, dt=5e-3)
     assert relerr_nodes(y1[sel], ref).max() < TOL_STEP
+
+
+@pytest.mark.parametrize("L,terms", [(8, ("lrot", "reg")), (6, ("lrot", "ddrx", "reg")), (10, ("lrot", "reg"))])
+@pytest.mark.parametrize("scheme", ["euler", "rk4"])
+def test_reduced_kernel_and_its_fallback(L, terms, scheme):
+    """The default kernels for these (L, terms) compute only the rows m >= 0 when a 32-node tile has the real-ODF
+    symmetry bit for bit, and fall back to the full two-lane algorithm for the tile otherwise
+    (csrc/sfb_step_kernel_r.cuh).  Mixed batches: symmetric tiles, general tiles, tiles with ONE asymmetric node,
+    a ragged tail; in-place stepping; exact symmetry of the output."""
+    import specfab_b200 as sf
+    if L not in built_L():
+        pytest.skip("L=%d not built" % L)
+    lm, n = sf.init(L)
+    N = 32 * 5 + 13
+    x = random_states(L, N, 700 + L, True)
+    xg = random_states(L, N, 701 + L, False)
+    x[32:64] = xg[32:64]                  # tile 1: general complex states
+    x[70] = xg[70]                        # tile 2: one general node among symmetric ones
+    x[100, 0] += 1e-3j                    # tile 3: Im n_0^0 != 0 only
+    x[130, n - 1] += 1e-9                 # tile 4: one coefficient off its mirror by more than round-off
+    x[140, 3] += 1e-18j                   # tile 4: round-off sized asymmetry (treated as a real ODF)
+    ug = random_ugrad(N, 702 + L)
+    tau = random_tau(N, 703 + L)
+    dt = 3.912e-3
+    ddrx = "ddrx" in terms
+    got = sf.step_arr(x, ug, tau if ddrx else None, dt=dt, Gamma0=4.0, terms=terms, scheme=scheme)
+    ref = oracle_steps(L, x, ug, tau if ddrx else None, scheme, 1, dt=dt, Gamma0=4.0, use_ddrx=ddrx)
+    assert relerr_nodes(got, ref).max() < TOL_STEP
+    # symmetric nodes stay symmetric bit for bit (so the next step takes the reduced path again)
+    idx = {k: j for j, k in enumerate(zip(lm[0].tolist(), lm[1].tolist()))}
+    sym_nodes = [p for p in range(N) if p < 32 or p >= 160]          # tiles 0 and 5 took the reduced path
+    for (l, m), j in idx.items():
+        if m > 0:
+            assert np.array_equal(got[sym_nodes, idx[(l, -m)]], (-1) ** m * np.conj(got[sym_nodes, j]))
+        if m == 0:
+            assert np.all(got[sym_nodes, j].imag == 0)
+    # in-place on the device gives the same bits
+    import torch
+    d = sf.layout_nlm(torch.from_numpy(x).cuda())
+    dug = sf.layout_mat(torch.from_numpy(ug).cuda())
+    dtau = sf.layout_mat(torch.from_numpy(tau).cuda()) if ddrx else None
+    sf.step_arr_dev(d, dug, dtau, dt=dt, Gamma0=4.0, terms=terms, scheme=scheme, out=d)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().T, got)

@@ -6,12 +6,19 @@ import specfab_b200 as sf
 from specfab_b200 import _lib
 
 
-def run(L, N, terms, scheme, variants, steps=10):
+def run(L, N, terms, scheme, variants, steps=10, physical=True):
     lm, n = sf.init(L)
     g = torch.Generator(device="cuda").manual_seed(1)
     nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
     nlm[0] = 0.2820947917738781
     nlm[1:] = 1e-2 * torch.view_as_complex(torch.randn((n - 1, N, 2), dtype=torch.float64, device="cuda", generator=g))
+    if physical:      # real-ODF symmetry n_l^-m = (-1)^m conj(n_l^m), Im n_l^0 = 0 (what the reduced kernels detect)
+        j = 0
+        for l in range(0, L + 1, 2):
+            base = l * (l + 1) // 2
+            nlm[base] = nlm[base].real.to(torch.complex128)
+            for m in range(1, l + 1):
+                nlm[base - m] = (-1) ** m * nlm[base + m].conj()
     ug = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
     tau = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
     tau = (tau + tau.permute(1, 0, 2)) / 2
@@ -44,7 +51,7 @@ def run(L, N, terms, scheme, variants, steps=10):
         k = info[key]
         nst = 4 if scheme == "rk4" else 1
         rate = N / (ms * 1e-3)
-        print(json.dumps(dict(L=L, terms="+".join(terms), scheme=scheme, variant=v, roles=k["roles"], tile=k["tile"], ms=round(ms, 4),
+        print(json.dumps(dict(L=L, terms="+".join(terms), scheme=scheme, physical=physical, variant=v, roles=k["roles"], tile=k["tile"], ms=round(ms, 4),
                               rate=round(rate / 1e6, 1), tflops=round(2 * k["dfma_per_node_rhs"] * nst * rate / 1e12, 2), diff_vs_v0=err)), flush=True)
     _lib.load().sfb_set_variant(0)
 
@@ -52,6 +59,18 @@ def run(L, N, terms, scheme, variants, steps=10):
 if __name__ == "__main__":
     V = list(range(0, 40))
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if len(sys.argv) > 2:
+        V = [int(x) for x in sys.argv[2].split(",")]
+    if which == "small":
+        for L in (4, 6, 10):
+            run(L, 1_000_000, ("lrot", "reg"), "rk4", V)
+            run(L, 1_000_000, ("lrot", "reg"), "euler", V)
+            run(L, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
+            run(L, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
+    if which == "8g":       # general complex states: the reduced kernels must take their in-kernel fallback
+        run(8, 200_000, ("lrot", "reg"), "rk4", V, physical=False)
+        run(8, 200_000, ("lrot", "ddrx", "reg"), "rk4", V, physical=False)
+        run(8, 200_000, ("lrot", "ddrx", "reg"), "euler", V, physical=False)
     if which in ("all", "8"):
         run(8, 1_000_000, ("lrot", "reg"), "rk4", V)
         run(8, 1_000_000, ("lrot", "reg"), "euler", V)
