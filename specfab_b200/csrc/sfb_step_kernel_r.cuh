@@ -120,6 +120,19 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
     }
+    // ---- the mirror rows (m < 0) of this lane's node, for the symmetry test: issued now, all loads in flight together,
+    // consumed after the tile has landed (their latency hides behind the bulk copies and the forcing preparation)
+    constexpr int kNNeg = kNCoef - kNRowR;
+    constexpr bool kBatchAll = kNNeg <= 42 && !SFB_DDRX;   // LROT kernels up to L = 12: every mirror row in registers
+                                                         // (the DDRX preparation needs the registers: per-degree batches there)
+    double2 vneg[kBatchAll ? (kNNeg > 0 ? kNNeg : 1) : 1];
+    const double2* gneg = P.nlm_in + node0 + (valid ? t : 0);
+    if (kBatchAll) {
+#pragma unroll
+        for (int l = 2; l <= kL; l += 2)
+#pragma unroll
+            for (int m = 1; m <= l; ++m) vneg[(l / 2) * (l / 2 - 1) + m - 1] = gneg[(long long)(hrow(l) - m) * P.ld_in];
+    }
     // ---- meanwhile: per-node forcing (lane set A only)
     if (valid) {
         const ForcSrc S = global_src(P, node0 + t);
@@ -140,19 +153,27 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
 
     // ---- real-ODF symmetry of the input to round-off (NaNs fail the test and take the general path)
     bool bad = false;
-    if (valid) {
-        const double2* gin = P.nlm_in + node0 + t;
+    {
         const double tol = kSymTol * fabs(bufs[t].x);
-#pragma unroll 1
+#pragma unroll
         for (int l = 0; l <= kL; l += 2) {
             bad |= !(fabs(bufs[(size_t)pslot(l, 0) * kTNR + t].y) <= tol);
-            for (int m = 1; m <= l; ++m) {
-                const double2 vp = bufs[(size_t)pslot(l, m) * kTNR + t];
-                const double2 vn = gin[(long long)(hrow(l) - m) * P.ld_in];
-                const double er = (m & 1) ? -vp.x : vp.x, ei = (m & 1) ? vp.y : -vp.y;
-                bad |= !(fabs(vn.x - er) <= tol && fabs(vn.y - ei) <= tol);
+            double2 vl[kL > 0 ? kL : 1];
+            if (!kBatchAll) {
+#pragma unroll
+                for (int m = 1; m <= kL; ++m)
+                    if (m <= l) vl[m - 1] = gneg[(long long)(hrow(l) - m) * P.ld_in];
             }
+#pragma unroll
+            for (int m = 1; m <= kL; ++m)
+                if (m <= l) {
+                    const double2 vp = bufs[(size_t)pslot(l, m) * kTNR + t];
+                    const double2 vn = kBatchAll ? vneg[(l / 2) * (l / 2 - 1) + m - 1] : vl[m - 1];
+                    const double er = (m & 1) ? -vp.x : vp.x, ei = (m & 1) ? vp.y : -vp.y;
+                    bad |= !(fabs(vn.x - er) <= tol && fabs(vn.y - ei) <= tol);
+                }
         }
+        bad = bad && valid;
     }
     if (__any_sync(0xffffffffu, bad)) {
         if (t == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");

@@ -14,6 +14,12 @@ g = torch.Generator(device="cuda").manual_seed(1)
 nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
 nlm[0] = 0.2820947917738781
 nlm[1:] = 1e-3 * torch.view_as_complex(torch.randn((n - 1, N, 2), dtype=torch.float64, device="cuda", generator=g))
+if os.environ.get("SFB_GENERAL_STATES", "0") != "1":      # real-ODF symmetry (what the reduced kernels detect)
+    for l in range(0, L + 1, 2):
+        base = l * (l + 1) // 2
+        nlm[base] = nlm[base].real.to(torch.complex128)
+        for m in range(1, l + 1):
+            nlm[base - m] = (-1) ** m * nlm[base + m].conj()
 ug = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
 tau = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
 tau = (tau + tau.permute(1, 0, 2)) / 2
