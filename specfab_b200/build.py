@@ -40,17 +40,18 @@ EXTRA = {
     (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
              (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False),
-             (25, -3, 32, 4, "imm", False), (26, -3, 32, 3, "imm", False), (27, -3, 32, 5, "imm", False)],
+             (25, -3, 32, 4, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (28, -4, 32, 5, "imm+ch2+r4", False)],
     (4, 0): [(25, -3, 32, 8, "imm", False)], (4, 1): [(25, -3, 32, 8, "imm", False)],
     (6, 0): [(25, -3, 32, 8, "imm", False)], (6, 1): [(25, -3, 32, 6, "imm", False)],
-    (10, 0): [(25, -3, 32, 5, "imm", False)], (10, 1): [(25, -3, 32, 3, "imm", False)],
-    (12, 0): [(25, -3, 32, 4, "imm", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
+    (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False)],
+    (10, 1): [(25, -3, 32, 3, "imm", False), (26, -4, 32, 4, "imm+ch2+r3", False), (27, -4, 32, 4, "imm+ch2+r4", False), (28, -4, 32, 4, "imm+ch2+r2", False)],
+    (12, 0): [(26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
               (1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
-    (12, 1): [(25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
+    (12, 1): [(26, -4, 32, 3, "imm+ch2+r4", False), (27, -4, 32, 3, "imm+ch2+r2", False), (28, -4, 32, 4, "imm+ch2+r3", False), (25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
               (10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
-    (20, 0): [(2, 5, 16, 3, "imm", False), (3, 4, 16, 3, "imm", False), (4, 7, 16, 2, "imm", False),
+    (20, 0): [(26, -4, 32, 3, "imm+ch2+r6", False), (27, -4, 32, 3, "imm+ch2+r4", False), (2, 5, 16, 3, "imm", False), (3, 4, 16, 3, "imm", False), (4, 7, 16, 2, "imm", False),
               (1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],
-    (20, 1): [(2, 8, 16, 2, "imm", False), (3, 6, 16, 2, "imm", False), (4, 4, 16, 2, "imm", False), (5, 10, 16, 2, "imm", False),
+    (20, 1): [(26, -4, 32, 2, "imm+ch2+r6", False), (27, -4, 32, 2, "imm+ch2+r4", False), (28, -4, 32, 2, "imm+ch2+r8", False), (2, 8, 16, 2, "imm", False), (3, 6, 16, 2, "imm", False), (4, 4, 16, 2, "imm", False), (5, 10, 16, 2, "imm", False),
               (1, 2, 16, 2, "imm", False), (20, -1, 32, 1, "imm", True), (30, -2, 16, 2, "imm+ch4+r6", False), (31, -2, 16, 2, "imm+ch2+r8", False)],
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
@@ -63,25 +64,30 @@ TUNE = {
     (4, 0): (-3, 32, 8, "imm", False), (4, 1): (-3, 32, 8, "imm", False),
     (6, 0): (-3, 32, 8, "imm", False), (6, 1): (-3, 32, 6, "imm", False),
     (8, 0): (-3, 32, 7, "imm", False), (8, 1): (0, 64, 2, "imm", False),
-    (10, 0): (-3, 32, 5, "imm", False), (10, 1): (-2, 32, 2, "imm+ch2+r4", False),
-    (12, 0): (-3, 32, 4, "imm", False), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
-    (14, 0): (-2, 16, 4, "imm+ch2+r4", False), (14, 1): (-2, 16, 3, "imm+ch2+r4", False),
-    (16, 0): (-2, 16, 4, "imm+ch2+r6", False), (16, 1): (-2, 16, 3, "imm+ch2+r6", False),
-    (18, 0): (-2, 16, 3, "imm+ch2+r6", False), (18, 1): (-2, 16, 2, "imm+ch2+r6", False),
-    (20, 0): (-2, 16, 3, "imm+ch2+r6", False), (20, 1): (-2, 16, 2, "imm+ch2+r6", False),
+    (10, 0): (-3, 32, 5, "imm", False), (10, 1): (-4, 32, 4, "imm+ch2+r3", False),
+    (12, 0): (-3, 32, 4, "imm", False), (12, 1): (-4, 32, 4, "imm+ch2+r3", False),
+    (14, 0): (-4, 32, 4, "imm+ch2+r4", False), (14, 1): (-4, 32, 3, "imm+ch2+r4", False),
+    (16, 0): (-4, 32, 4, "imm+ch2+r4", False), (16, 1): (-4, 32, 3, "imm+ch2+r6", False),
+    (18, 0): (-4, 32, 3, "imm+ch2+r4", False), (18, 1): (-4, 32, 2, "imm+ch2+r6", False),
+    (20, 0): (-4, 32, 3, "imm+ch2+r4", False), (20, 1): (-4, 32, 2, "imm+ch2+r6", False),
 }
 
 
 # scheme-specific default: variant 100 (when present) replaces variant 0 for multi-stage (RK4) steps -- with DDRX the
 # classical RK4 keeps three state buffers, which favours the reduced kernel's halved footprint
 TUNE_RK = {
-    (8, 1): (-3, 32, 4, "imm", False), (10, 1): (-3, 32, 3, "imm", False),
+    (8, 1): (-3, 32, 4, "imm", False),
 }
 # the previous full-form defaults stay selectable (variant 40) for comparisons
 FULL_DEFAULT = {
     (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
     (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
     (8, 0): (1, 16, 6, "imm", False), (10, 0): (0, 16, 4, "imm+w", True), (12, 0): (0, 16, 4, "imm+w", True),
+    (10, 1): (-2, 32, 2, "imm+ch2+r4", False), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
+    (14, 0): (-2, 16, 4, "imm+ch2+r4", False), (14, 1): (-2, 16, 3, "imm+ch2+r4", False),
+    (16, 0): (-2, 16, 4, "imm+ch2+r6", False), (16, 1): (-2, 16, 3, "imm+ch2+r6", False),
+    (18, 0): (-2, 16, 3, "imm+ch2+r6", False), (18, 1): (-2, 16, 2, "imm+ch2+r6", False),
+    (20, 0): (-2, 16, 3, "imm+ch2+r6", False), (20, 1): (-2, 16, 2, "imm+ch2+r6", False),
 }
 
 
@@ -126,6 +132,18 @@ def generate(Ls):
                     skeleton = "sfb_step_kernel.cuh"
                     R = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])     # warp roles per node group
                     meta["R"] = R
+                elif R == -4:      # reduced table-driven loop kernel (one lane per node, +rN roles, +chN rows/chunk), loop-form fallback
+                    ch = max([int(x[2:]) for x in parts[1:] if x.startswith("ch")] + [2])
+                    tabsrc, meta = emit_step.emit_loop_table(L, dd, ch)
+                    meta.update(TN=TN, dfma_role=[0], dfma_node=sum(p.dfma for p in emit_step.plan(L, dd)[1]), loads_node=0, nrow=emit_step.nrow_phys(L))
+                    meta["dfma_node_full"] = 2 * meta["dfma_node"]
+                    meta["reduced"] = 1
+                    body = "// loop kernel: no generated body\n"
+                    R = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])
+                    meta["R"] = R
+                    tab = "#define SFB_LOOP 1\n#define SFB_CH %d\n#define SFB_REDUCED 1\n#define SFB_TNR %d\n" % (ch, TN) + tabsrc
+                    skeleton = "sfb_step_kernel.cuh"
+                    R_cu, TN_cu, inc_cu = R, 16, "gen/apply_%s.inc" % tag
                 elif R == -3:      # reduced one-lane kernel for real-ODF states (+ in-kernel two-lane fallback, tiles of 16)
                     body, tab, meta = emit_step.emit(L, dd, 1, TN, cm, False, mc, gd, reduced=True)
                     fbody, _, fmeta = emit_step.emit(L, dd, 1, 16, cm, False, mc, gd)

@@ -20,9 +20,14 @@ namespace {
 constexpr int kTNR = SFB_TNR;
 constexpr double kSymTol = 0x1p-46;
 constexpr int kNRowR = (kL / 2 + 1) * (kL / 2 + 1);       // rows (l, m >= 0)
-static_assert(kTNR == 32 && kTN == 16 && kR == 1 && kThreads == 32, "reduced kernel: one warp, 32 nodes, fallback tiles of 16");
+// one lane per node; kR warp roles share the 32 nodes of the tile (straight-line form: kR = 1, no barriers at all;
+// table-driven loop form: the (mu, chunk) items are dealt to the roles).  The fallback runs full_tile() with the same
+// kThreads = 32 * kR threads on tiles of 16 nodes.
+static_assert(kTNR == 32 && kTN == 16 && kThreads == 32 * kR, "reduced kernel: 32 nodes per CTA, fallback tiles of 16");
 
 struct CtxR {
+    const double2* ktab;              // loop mode: global table of operator entries
+    double2* ring;                    // loop mode: this warp's private table ring in shared memory
     const double2* yp;                // stage input, rows pslot(l, m) * kTNR
     const double2* fz;                // forcing block (lane set A's)
     double2* op;                      // next-stage buffer
@@ -77,34 +82,41 @@ __device__ __forceinline__ void row_out_r(const CtxR& c, double kr, double ki, d
 #define SFB_RROW_PRE(l, mu, q, r) const double2 q = n0_load_r<l, mu>(c), r = acc_load_r<l, mu>(c)
 #define SFB_RROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out_r<l, mu>(c, ar, ai, zr, zi, q, r)
 
-__device__ __forceinline__ void apply_reduced(const CtxR& c) {
+#ifdef SFB_LOOP
+#include "sfb_step_loop_r.cuh"
+__device__ __forceinline__ void apply_reduced(const CtxR& c, int role) { loopk::apply_loop_r(c, role, kR, c.ring, (int)(threadIdx.x & 31)); }
+#else
+__device__ __forceinline__ void apply_reduced(const CtxR& c, int role) {
     const double2* __restrict__ yp = c.yp;
     const double2* __restrict__ fz = c.fz;
-    const int role = 0;
 #include SFB_APPLY_INC_R
 }
+#endif
 
-__global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParams P) {
+__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbStepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nbuf = P.nstage == 1 ? 1 : (SFB_HORNER ? 2 : 3);
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* forc = bufs + (size_t)nbuf * kNRowR * kTNR;
     double* scal = reinterpret_cast<double*>(forc + kNF * kTNR);
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(scal + kNSc * kTNR);
+    double2* rings = reinterpret_cast<double2*>(mbar + 2);          // loop mode: [warps][2][pairs per item]
+    (void)rings;
 
-    const int t = threadIdx.x;                        // node within tile
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int t = tid & 31;                           // node within tile
     const long long node0 = (long long)blockIdx.x * kTNR;
     const int nvalid = (int)min((long long)kTNR, P.N - node0);
     const bool valid = t < nvalid;
 
     // ---- stage the rows m >= 0 of the tile (one bulk copy per row) into buffer 0
     const uint32_t mb = smem_u32(mbar);
-    if (t == 0) {
+    if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    {
+    __syncthreads();
+    if (warp == 0) {
         const uint32_t bytes = (uint32_t)nvalid * 16u;
         if (t == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes * (uint32_t)kNRowR) : "memory");
@@ -120,26 +132,26 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
     }
-    // ---- the mirror rows (m < 0) of this lane's node, for the symmetry test: issued now, all loads in flight together,
-    // consumed after the tile has landed (their latency hides behind the bulk copies and the forcing preparation)
+    // ---- the mirror rows (m < 0) of this lane's node, for the symmetry test (warp 0): issued now, all loads in flight
+    // together, consumed after the tile has landed (their latency hides behind the bulk copies and the forcing preparation)
     constexpr int kNNeg = kNCoef - kNRowR;
     constexpr bool kBatchAll = kNNeg <= 42 && !SFB_DDRX;   // LROT kernels up to L = 12: every mirror row in registers
                                                          // (the DDRX preparation needs the registers: per-degree batches there)
     double2 vneg[kBatchAll ? (kNNeg > 0 ? kNNeg : 1) : 1];
     const double2* gneg = P.nlm_in + node0 + (valid ? t : 0);
-    if (kBatchAll) {
+    if (kBatchAll && warp == 0) {
 #pragma unroll
         for (int l = 2; l <= kL; l += 2)
 #pragma unroll
             for (int m = 1; m <= l; ++m) vneg[(l / 2) * (l / 2 - 1) + m - 1] = gneg[(long long)(hrow(l) - m) * P.ld_in];
     }
-    // ---- meanwhile: per-node forcing (lane set A only)
+    // ---- meanwhile: per-node forcing (lane set A only); with several roles the tasks go to different warps
     if (valid) {
         const ForcSrc S = global_src(P, node0 + t);
-        prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal);
+        if (warp == 0) prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal);
 #if SFB_DDRX
-        prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
-        prep_ddrx_d<kTNR>(S, t, scal);
+        if (warp == (kR > 1 ? 1 : 0)) prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
+        if (warp == (kR > 2 ? 2 : 0)) prep_ddrx_d<kTNR>(S, t, scal);
 #endif
     }
     {   // wait for the tile
@@ -149,11 +161,10 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
                          : "=r"(done) : "r"(mb) : "memory");
         }
     }
-    __syncwarp();
 
     // ---- real-ODF symmetry of the input to round-off (NaNs fail the test and take the general path)
     bool bad = false;
-    {
+    if (warp == 0) {
         const double tol = kSymTol * fabs(bufs[t].x);
 #pragma unroll
         for (int l = 0; l <= kL; l += 2) {
@@ -175,15 +186,22 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
         }
         bad = bad && valid;
     }
-    if (__any_sync(0xffffffffu, bad)) {
-        if (t == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
-        __syncwarp();
+    if (__syncthreads_or(bad)) {     // also orders the forcing preparation before the stages
+        if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
+        __syncthreads();
         full_tile(P, node0, smem_raw);
         if (node0 + kTN < P.N) full_tile(P, node0 + kTN, smem_raw);
         return;
     }
 
     CtxR c;
+#ifdef SFB_LOOP
+    c.ring = rings + (size_t)warp * 2 * (SFB_LT_PER_CHUNK / 2);
+    c.ktab = P.ktab;
+#else
+    c.ring = nullptr;
+    c.ktab = nullptr;
+#endif
     c.valid = valid;
     c.fz = forc + t;
     c.lam = scal[SC_LAM * kTNR + t];
@@ -214,22 +232,30 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
         }
 #endif
 #if SFB_DDRX
-        if (valid) {   // <D>(current stage state)
-            const double2* y = c.yp;
-            double2 n2[3], n4[5];
+        if (kR == 1 || warp == 0) {   // <D>(current stage state), one lane per node
+            if (valid) {
+                const double2* y = c.yp;
+                double2 n2[3], n4[5];
 #pragma unroll
-            for (int m = 0; m < 3; ++m) n2[m] = y[pslot(2, m) * kTNR];
+                for (int m = 0; m < 3; ++m) n2[m] = y[pslot(2, m) * kTNR];
 #pragma unroll
-            for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[pslot(4, m) * kTNR] : make_double2(0.0, 0.0);
-            double tv[6], sv[6];
+                for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[pslot(4, m) * kTNR] : make_double2(0.0, 0.0);
+                double tv[6], sv[6];
 #pragma unroll
-            for (int p = 0; p < 6; ++p) { tv[p] = scal[(SC_TAUV + p) * kTNR + t]; sv[p] = scal[(SC_TSQV + p) * kTNR + t]; }
-            const double davg = sfb::ev_D2(y[0], n2, n4, tv, sv, scal[SC_NORM * kTNR + t]);
-            c.c0 = -(scal[SC_G0 * kTNR + t] * davg);
+                for (int p = 0; p < 6; ++p) { tv[p] = scal[(SC_TAUV + p) * kTNR + t]; sv[p] = scal[(SC_TSQV + p) * kTNR + t]; }
+                const double davg = sfb::ev_D2(y[0], n2, n4, tv, sv, scal[SC_NORM * kTNR + t]);
+                c.c0 = -(scal[SC_G0 * kTNR + t] * davg);
+                if (kR > 1) scal[SC_C0 * kTNR + t] = c.c0;
+            }
+        }
+        if (kR > 1) {
+            __syncthreads();
+            c.c0 = scal[SC_C0 * kTNR + t];
         }
 #endif
-        apply_reduced(c);
-        // every lane reads and writes only its own node's column: no barrier between stages
+        apply_reduced(c, warp);
+        // one role: every lane reads and writes only its own node's column -- no barrier between stages
+        if (kR > 1 && !c.last) __syncthreads();
     }
 }
 
@@ -237,7 +263,7 @@ __global__ void __launch_bounds__(32, SFB_MINB) step_kernel_r(const SfbStepParam
 
 extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
     static bool attr_done[64] = {false};
-    const size_t fixed = (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16;
+    const size_t fixed = (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16 + kRingBytes;
     const size_t per_buf = (size_t)kNRowR * kTNR * 16;
     const int nbuf_rk = SFB_HORNER ? 2 : 3;
     const size_t smem_max = nbuf_rk * per_buf + fixed;
@@ -254,6 +280,9 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         attr_done[dev] = true;
     }
     SfbStepParams P = Pin;
+#ifdef SFB_LOOP
+    { void* tp = nullptr; e = cudaGetSymbolAddress(&tp, sfb_ltab); if (e != cudaSuccess) return e; P.ktab = reinterpret_cast<const double2*>(tp); }
+#endif
     P.n0_global = 1;
     const int nbuf = P.nstage == 1 ? 1 : nbuf_rk;
     const size_t smem = nbuf * per_buf + fixed;
@@ -269,6 +298,6 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     }
     if (P.N <= 0) return cudaSuccess;
     const long long ntile = (P.N + kTNR - 1) / kTNR;
-    step_kernel_r<<<(unsigned)ntile, 32, smem, st>>>(P);
+    step_kernel_r<<<(unsigned)ntile, kThreads, smem, st>>>(P);
     return cudaGetLastError();
 }

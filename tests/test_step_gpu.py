@@ -51,15 +51,17 @@ def test_step_lrot_reg(L, scheme, physical):
     assert relerr_nodes(got, ref).max() < TOL_STEP
 
 
-@pytest.mark.parametrize("L", [4, 8, 12, 20])
+@pytest.mark.parametrize("L", [4, 8, 10, 12, 20])
 @pytest.mark.parametrize("scheme", ["euler", "rk4"])
-def test_step_all_terms(L, scheme):
+@pytest.mark.parametrize("physical", [True, False])
+def test_step_all_terms(L, scheme, physical):
+    """physical states take the reduced (m >= 0) kernels, general complex states their in-kernel full fallback"""
     import specfab_b200 as sf
     if L not in built_L():
         pytest.skip("L=%d not built" % L)
     N = 45 if L <= 12 else 19
     sf.init(L)
-    x = random_states(L, N, 300 + L, True)
+    x = random_states(L, N, 300 + L, physical)
     ug = random_ugrad(N, 400 + L)
     tau = random_tau(N, 500 + L)
     dt = 3.912e-3

@@ -67,6 +67,15 @@ if __name__ == "__main__":
             run(L, 1_000_000, ("lrot", "reg"), "euler", V)
             run(L, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
             run(L, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
+    if which == "mid":
+        run(8, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
+        run(10, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
+        run(10, 1_000_000, ("lrot", "reg"), "rk4", V)
+        run(12, 500_000, ("lrot", "reg"), "rk4", V)
+        run(12, 500_000, ("lrot", "reg"), "euler", V)
+        for L in (14, 16, 18):
+            run(L, 300_000, ("lrot", "ddrx", "cdrx", "reg"), "euler", V)
+            run(L, 300_000, ("lrot", "reg"), "euler", V)
     if which == "8g":       # general complex states: the reduced kernels must take their in-kernel fallback
         run(8, 200_000, ("lrot", "reg"), "rk4", V, physical=False)
         run(8, 200_000, ("lrot", "ddrx", "reg"), "rk4", V, physical=False)
