@@ -331,8 +331,15 @@ def main():
         roof = {"bound": "fp64", "achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc}
     else:
         roof = {"bound": "hbm", "achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc}
-    roof.update({"traffic": traffic, "kernel": "step_kernel (L=%d, %s, %s)" % (L, "+".join(terms), scheme),
+    reduced = info["roles"] >= 1 and info["tile"] == 32 and any(
+        k["L"] == L and k["ddrx"] == info["ddrx"] and k["variant"] == 40 for k in sf.build_info()["step_kernels"])
+    full = [k for k in sf.build_info()["step_kernels"] if k["L"] == L and k["ddrx"] == info["ddrx"] and k["variant"] == 40]
+    roof.update({"traffic": traffic,
+                 "kernel": "%s (L=%d, %s, %s)" % ("step_kernel_r" if reduced else "step_kernel", L, "+".join(terms), scheme),
+                 "form": ("reduced: only the rows m >= 0 are computed (real-ODF symmetry of every 32-node tile verified in the kernel, "
+                          "full-form fallback otherwise; SURVEY.md 8d: flop counts scaled accordingly)") if reduced else "full",
                  "flops_per_node_step_executed": 2 * info["dfma_per_node_rhs"] * nst,
+                 "flops_per_node_step_full_form": (2 * full[0]["dfma_per_node_rhs"] * nst) if full else None,
                  "alg_bytes_per_node_step": alg_bytes_per_node_step(n, terms, eij),
                  "hbm": {"achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc},
                  "fp64": {"achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc},

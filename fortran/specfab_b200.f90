@@ -53,6 +53,34 @@ module specfab_b200
             real(c_double), value :: alpha
             integer(c_int), value :: n_grain
         end function
+        integer(c_int) function sfb_Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3, N, ld, e1, e2, e3, Eij_grain, alpha, n_grain, Eij) &
+                bind(c, name='sfb_Eij_orthotropic_arr')                                   ! src/specfabpy.f90:488
+            import; type(c_ptr), value :: nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij
+            integer(c_int64_t), value :: N, ld
+            real(c_double), intent(in) :: Eij_grain(6)
+            real(c_double), value :: alpha
+            integer(c_int), value :: n_grain
+        end function
+        integer(c_int) function sfb_E_CAFFE_arr(nlm, N, ld, eps, Emin, Emax, n_grain, E) bind(c, name='sfb_E_CAFFE_arr')  ! src/specfabpy.f90:543
+            import; type(c_ptr), value :: nlm, eps, E; integer(c_int64_t), value :: N, ld
+            real(c_double), value :: Emin, Emax; integer(c_int), value :: n_grain
+        end function
+        integer(c_int) function sfb_M_LROT_reduced_arr(eps, omg, N, iota, zeta, Mrr, Mri, Mir, Mii) &
+                bind(c, name='sfb_M_LROT_reduced_arr')                                    ! src/reducedform.f90:76 of src/dynamics.f90:52
+            import; type(c_ptr), value :: eps, omg, Mrr, Mri, Mir, Mii; integer(c_int64_t), value :: N
+            real(c_double), value :: iota, zeta
+        end function
+        integer(c_int) function sfb_M_DDRX_reduced_arr(nlm, ld_nlm, tau, N, src_only, Mrr, Mri, Mir, Mii) &
+                bind(c, name='sfb_M_DDRX_reduced_arr')                                    ! src/reducedform.f90:76 of src/dynamics.f90:251
+            import; type(c_ptr), value :: nlm, tau, Mrr, Mri, Mir, Mii; integer(c_int64_t), value :: ld_nlm, N
+            integer(c_int), value :: src_only
+        end function
+        integer(c_int) function sfb_apply_bounds_arr(nlm_in, nlm_out, N, ld) bind(c, name='sfb_apply_bounds_arr')   ! src/dynamics.f90:530
+            import; type(c_ptr), value :: nlm_in, nlm_out; integer(c_int64_t), value :: N, ld
+        end function
+        integer(c_int) function sfb_ai_to_nlm_arr(rank, a, N, nlm) bind(c, name='sfb_ai_to_nlm_arr')               ! src/moments.f90:68-92
+            import; integer(c_int), value :: rank; type(c_ptr), value :: a, nlm; integer(c_int64_t), value :: N
+        end function
     end interface
 
 contains
@@ -89,6 +117,29 @@ contains
         call check(sfb_Eij_tranisotropic_arr(c_loc(nlm), int(size(nlm,1),c_int64_t), int(size(nlm,1),c_int64_t), &
                    c_loc(e1), c_loc(e2), c_loc(e3), Eij_grain, alpha, int(n_grain,c_int), c_loc(Eij), c_null_ptr), &
                    'Eij_tranisotropic_arr')
+    end function
+
+    ! drop-in for Eij_orthotropic_arr (src/specfabpy.f90:488-500)
+    function Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3, e1,e2,e3, Eij_grain,alpha,n_grain) result(Eij)
+        complex(kind=dp), intent(in), target :: nlm_1(:,:), nlm_2(:,:), nlm_3(:,:)
+        real(kind=dp), intent(in), target    :: e1(size(nlm_1,1),3), e2(size(nlm_1,1),3), e3(size(nlm_1,1),3)
+        real(kind=dp), intent(in)            :: Eij_grain(6), alpha
+        integer, intent(in)                  :: n_grain
+        real(kind=dp), target                :: Eij(size(nlm_1,1),6)
+        call check(sfb_Eij_orthotropic_arr(c_loc(nlm_1), c_loc(nlm_2), c_loc(nlm_3), int(size(nlm_1,1),c_int64_t), &
+                   int(size(nlm_1,1),c_int64_t), c_loc(e1), c_loc(e2), c_loc(e3), Eij_grain, alpha, int(n_grain,c_int), c_loc(Eij)), &
+                   'Eij_orthotropic_arr')
+    end function
+
+    ! drop-in for E_CAFFE_arr (src/specfabpy.f90:543-554)
+    function E_CAFFE_arr(nlm, eps, Emin, Emax, n_grain) result(E)
+        complex(kind=dp), intent(in), target :: nlm(:,:)
+        real(kind=dp), intent(in), target    :: eps(size(nlm,1),3,3)
+        real(kind=dp), intent(in)            :: Emin, Emax
+        integer, intent(in)                  :: n_grain
+        real(kind=dp), target                :: E(size(nlm,1))
+        call check(sfb_E_CAFFE_arr(c_loc(nlm), int(size(nlm,1),c_int64_t), int(size(nlm,1),c_int64_t), c_loc(eps), Emin, Emax, &
+                   int(n_grain,c_int), c_loc(E)), 'E_CAFFE_arr')
     end function
 
     ! scalar forms keep the reference signatures (N = 1 batches)
