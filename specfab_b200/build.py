@@ -36,11 +36,12 @@ EXTRA = {
     (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 2, 16, 7, "imm", False), (12, 2, 16, 6, "imm", False), (13, 2, 16, 5, "imm", False), (14, 2, 32, 3, "imm", False),
              (15, 3, 16, 7, "imm", False), (16, 2, 16, 7, "imm+c6", False),
-             (25, -3, 32, 7, "imm", False), (26, -3, 32, 6, "imm", False), (27, -3, 32, 5, "imm", False)],
+             (25, -3, 32, 7, "imm+r2", False), (26, -3, 32, 7, "imm+r3", False), (27, -3, 32, 7, "imm+c4", False), (28, -3, 32, 7, "imm+c8", False)],
     (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
              (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False),
-             (25, -3, 32, 4, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (28, -4, 32, 5, "imm+ch2+r4", False)],
+             (25, -3, 32, 4, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -3, 32, 4, "imm+r2", False), (28, -3, 32, 4, "imm+r3", False),
+             (29, -3, 32, 3, "imm+r4", False)],
     (4, 0): [(25, -3, 32, 8, "imm", False)], (4, 1): [(25, -3, 32, 8, "imm", False)],
     (6, 0): [(25, -3, 32, 8, "imm", False)], (6, 1): [(25, -3, 32, 6, "imm", False)],
     (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False)],
@@ -76,7 +77,7 @@ TUNE = {
 # scheme-specific default: variant 100 (when present) replaces variant 0 for multi-stage (RK4) steps -- with DDRX the
 # classical RK4 keeps three state buffers, which favours the reduced kernel's halved footprint
 TUNE_RK = {
-    (8, 1): (-3, 32, 4, "imm", False),
+    (8, 1): (-3, 32, 4, "imm+r3", False),
 }
 # the previous full-form defaults stay selectable (variant 40) for comparisons
 FULL_DEFAULT = {
@@ -145,14 +146,16 @@ def generate(Ls):
                     skeleton = "sfb_step_kernel.cuh"
                     R_cu, TN_cu, inc_cu = R, 16, "gen/apply_%s.inc" % tag
                 elif R == -3:      # reduced one-lane kernel for real-ODF states (+ in-kernel two-lane fallback, tiles of 16)
-                    body, tab, meta = emit_step.emit(L, dd, 1, TN, cm, False, mc, gd, reduced=True)
-                    fbody, _, fmeta = emit_step.emit(L, dd, 1, 16, cm, False, mc, gd)
+                    Rr = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])      # "+rN": warp roles sharing the 32 nodes
+                    body, tab, meta = emit_step.emit(L, dd, Rr, TN, cm, False, mc, gd, reduced=True)
+                    fbody, _, fmeta = emit_step.emit(L, dd, Rr, 16, cm, False, mc, gd)
                     _write_if_changed(os.path.join(GEN, "apply_%s_full.inc" % tag), fbody)
                     tab = ('#define SFB_REDUCED 1\n#define SFB_TNR %d\n#define SFB_APPLY_INC_R "gen/apply_%s.inc"\n' % (TN, tag)) + tab
                     skeleton = "sfb_step_kernel.cuh"
                     meta["dfma_node_full"] = fmeta["dfma_node"]
                     meta["reduced"] = 1
-                    R_cu, TN_cu, inc_cu = 1, 16, "gen/apply_%s_full.inc" % tag
+                    meta["R"] = Rr
+                    R_cu, TN_cu, inc_cu = Rr, 16, "gen/apply_%s_full.inc" % tag
                 elif R == -1:      # persistent, lock-stepped, streaming refill (four lanes per node)
                     body, tab, meta = emit_step.emit4(L, dd, TN, cm, True, window, mc, gd)
                     skeleton = "sfb_step_kernel5.cuh"
