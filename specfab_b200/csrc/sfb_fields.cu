@@ -1,4 +1,5 @@
 // Kernels + launchers for a2 / a4 / eigenframe / Eij on batches of nodes (thread per node).
+#include <cstdlib>
 #include "sfb_fields.cuh"
 
 namespace {
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(kBlock) eig_kernel(const double2* __restrict__
 
 // Eij_tranisotropic_arr (src/specfabpy.f90:474-486).  frame given (e1,e2,e3 each (N,3) Fortran order)
 // or, when e1 == nullptr, computed as the a2 eigenframe of the node (fused a2 -> eig -> Eij).
-__global__ void __launch_bounds__(kBlock) eij_kernel(const double2* __restrict__ nlm, long long N, long long ld,
+template <int MB>
+__global__ void __launch_bounds__(kBlock, MB) eij_kernel(const double2* __restrict__ nlm, long long N, long long ld,
                                                      const double* __restrict__ e1, const double* __restrict__ e2,
                                                      const double* __restrict__ e3, long long lde, sfb::EijCoef K,
                                                      double* __restrict__ Eij, long long ldo,
@@ -181,7 +183,13 @@ cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, lon
 cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
                            int* status, cudaStream_t st) {
-    if (N > 0) eij_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+    static int mb = 0;
+    if (!mb) { const char* ev = getenv("SFB_EIJ_MB"); mb = ev ? atoi(ev) : 4;      // 4 CTAs of 128 threads per SM (128 registers, a few spills) beats 2 x 255: the kernel is FP64-latency bound }
+    if (N > 0) {
+        if (mb == 3) eij_kernel<3><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+        else if (mb == 4) eij_kernel<4><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+        else eij_kernel<2><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+    }
     return cudaGetLastError();
 }
 

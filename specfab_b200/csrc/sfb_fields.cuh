@@ -244,6 +244,61 @@ __device__ __forceinline__ void potrs_lower(const double a[6][6], const double i
     }
 }
 
+// Taylor matrix P of src/homogenizations.f90:165-170 (full, non-symmetric)
+__device__ __forceinline__ void taylor_P(const double a2v[6], const double a4p[21], const EijCoef& K, double P[6][6]) {
+    double a2m[3][3];
+    vec_to_mat(a2v, a2m);
+    const double s = SFB_SQRT2;
+    const double Lm[6][6] = {
+        {2 * a2m[0][0], 0.0, 0.0, 0.0, s * a2m[0][2], s * a2m[0][1]},
+        {0.0, 2 * a2m[1][1], 0.0, s * a2m[1][2], 0.0, s * a2m[0][1]},
+        {0.0, 0.0, 2 * a2m[2][2], s * a2m[1][2], s * a2m[0][2], 0.0},
+        {0.0, s * a2m[1][2], s * a2m[1][2], a2m[1][1] + a2m[2][2], a2m[0][1], a2m[0][2]},
+        {s * a2m[0][2], 0.0, s * a2m[0][2], a2m[0][1], a2m[0][0] + a2m[2][2], a2m[1][2]},
+        {s * a2m[0][1], s * a2m[0][1], 0.0, a2m[0][2], a2m[1][2], a2m[0][0] + a2m[1][1]}};
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const double idv = (i < 3) ? 1.0 : 0.0;
+            P[i][j] = ((i == j ? 1.0 : 0.0) - K.tA * (idv * a2v[j])) + K.tB * a4p[i <= j ? tri6(i, j) : tri6(j, i)] + K.tC * Lm[i][j];
+        }
+}
+
+// The reference's ill-posed branch (src/homogenizations.f90:177-185): P_reg = P^T P + 1e-6 I built from the PARTIALLY
+// FACTORISED P that dposv leaves behind, rhs P^T tau.  Rare (unphysical states) and register hungry, so it is kept out
+// of line and redoes the factorisation; returns the status flags, x <- solution for the right-hand side tv.
+static __device__ __noinline__ int taylor_fallback_solve(const double a2v[6], const double a4p[21], const EijCoef& K, const double tv[6],
+                                                  double x[6]) {
+    double F[6][6];
+    taylor_P(a2v, a4p, K, F);
+    potf2_lower(F);
+    double R[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s += F[k][i] * F[k][j];
+            R[i][j] = s + (i == j ? 0x1.0c6f7ap-20 : 0.0);      // 1e-6 is a real(4) literal
+        }
+    int status = SFB_ST_TAYLOR_FALLBACK;
+    if (potf2_lower(R) != 0) status |= SFB_ST_TAYLOR_FAILED;
+    double invd[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) invd[i] = 1.0 / R[i][i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += F[k][i] * tv[k];
+        x[i] = s;
+    }
+    potrs_lower(R, invd, x);
+    return status;
+}
+
 // Eij = (E11,E22,E33,E23,E13,E12) w.r.t. the rows of e[3][3].  returns status flags.
 // SACHS_GIVEN: the six Sachs ratios come from the caller (n'=3 closure, sfb_moments_hi.cuh); the Taylor part is
 // always the n'=1 solve with the caller's coefficients (src/homogenizations.f90:148).
@@ -256,64 +311,48 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
     ev_c4_mandel(n00, n2, n4, a4p);
     double a2m[3][3];
     vec_to_mat(a2v, a2m);
-    // ---- Taylor matrix P (src/homogenizations.f90:165-170) and its Cholesky factor
-    double P[6][6];
-    {
-        const double s = SFB_SQRT2;
-        const double Lm[6][6] = {
-            {2 * a2m[0][0], 0.0, 0.0, 0.0, s * a2m[0][2], s * a2m[0][1]},
-            {0.0, 2 * a2m[1][1], 0.0, s * a2m[1][2], 0.0, s * a2m[0][1]},
-            {0.0, 0.0, 2 * a2m[2][2], s * a2m[1][2], s * a2m[0][2], 0.0},
-            {0.0, s * a2m[1][2], s * a2m[1][2], a2m[1][1] + a2m[2][2], a2m[0][1], a2m[0][2]},
-            {s * a2m[0][2], 0.0, s * a2m[0][2], a2m[0][1], a2m[0][0] + a2m[2][2], a2m[1][2]},
-            {s * a2m[0][1], s * a2m[0][1], 0.0, a2m[0][2], a2m[1][2], a2m[0][0] + a2m[1][1]}};
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const double idv = (i < 3) ? 1.0 : 0.0;
-                P[i][j] = ((i == j ? 1.0 : 0.0) - K.tA * (idv * a2v[j])) + K.tB * a4p[i <= j ? tri6(i, j) : tri6(j, i)] + K.tC * Lm[i][j];
-            }
-    }
+    // ---- Cholesky factor of the Taylor matrix: dposv('L') reads and writes the lower triangle only, so only that
+    // half is ever touched here (the unrolled code keeps 21 entries in registers, not 36)
     int status = 0;
     double F[6][6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) F[i][j] = P[i][j];
-    const int info = potf2_lower(F);
-    double R[6][6] = {};  // regularised normal matrix (only if the factorisation failed)
-    if (info != 0) {    // src/homogenizations.f90:177-185: P_reg = P^T P + 1e-6 I using the partially factorised P
-        status |= SFB_ST_TAYLOR_FALLBACK;
+    {
+        double P[6][6];
+        taylor_P(a2v, a4p, K, P);
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s += F[k][i] * F[k][j];
-                R[i][j] = s + (i == j ? 0x1.0c6f7ap-20 : 0.0);      // 1e-6 is a real(4) literal
-            }
-        if (potf2_lower(R) != 0) status |= SFB_ST_TAYLOR_FAILED;
+            for (int j = 0; j < 6; ++j)
+                if (j <= i) F[i][j] = P[i][j];
     }
+    const int info = potf2_lower(F);
     double invd[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) invd[i] = 1.0 / (info == 0 ? F[i][i] : R[i][i]);
+    for (int i = 0; i < 6; ++i) invd[i] = 1.0 / F[i][i];
     const double inv_t_iso = 1.0 / K.t_iso;
     bool finite = true;
+#ifdef SFB_EIJ_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int q = 0; q < 6; ++q) {
         // (v,w) pairs: 11,22,33,23,13,12   src/enhancementfactors.f90:36-44
         const int iv = (q < 3) ? q : (q == 3 ? 1 : 0);
         const int iw = (q < 3) ? q : (q == 5 ? 1 : 2);
+        double ev[3], ew[3];       // rows iv, iw of the frame, selected without local-memory indexing
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            ev[i] = iv == 0 ? e[0][i] : (iv == 1 ? e[1][i] : e[2][i]);
+            ew[i] = iw == 0 ? e[0][i] : (iw == 1 ? e[1][i] : e[2][i]);
+        }
         double tau[3][3], vw[3][3];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                vw[i][j] = e[iv][i] * e[iw][j];
-                if (q < 3) tau[i][j] = ((i == j) ? 1.0 / 3.0 : 0.0) - e[iv][i] * e[iv][j];   // tau_vv
-                else tau[i][j] = e[iv][i] * e[iw][j] + e[iw][i] * e[iv][j];                // tau_vw
+                vw[i][j] = ev[i] * ew[j];
+                tau[i][j] = q < 3 ? ((i == j) ? 1.0 / 3.0 : 0.0) - ev[i] * ev[j]      // tau_vv
+                                  : ev[i] * ew[j] + ew[i] * ev[j];                    // tau_vw
             }
         double tv[6];
         mat_to_vec(tau, tv);
@@ -354,15 +393,15 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
 #pragma unroll
             for (int i = 0; i < 6; ++i) x[i] = tv[i];
             potrs_lower(F, invd, x);
-        } else {
+        } else {      // cold path: hand COPIES to the out-of-line routine so that the hot arrays stay in registers
+            double a2c[6], a4c[21], tvc[6], xc[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                double s = 0.0;
+            for (int i = 0; i < 6; ++i) { a2c[i] = a2v[i]; tvc[i] = tv[i]; }
 #pragma unroll
-                for (int k = 0; k < 6; ++k) s += F[k][i] * tv[k];
-                x[i] = s;
-            }
-            potrs_lower(R, invd, x);
+            for (int i = 0; i < 21; ++i) a4c[i] = a4p[i];
+            status |= taylor_fallback_solve(a2c, a4c, K, tvc, xc);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) x[i] = xc[i];
         }
         double et[3][3], eti[3][3];
         vec_to_mat(x, et);
@@ -371,8 +410,11 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
 #pragma unroll
             for (int j = 0; j < 3; ++j) eti[i][j] = tau[i][j] * inv_t_iso;
         const double Et = dinner22(et, vw) / dinner22(eti, vw);
-        E[q] = (1 - K.alpha) * Es + K.alpha * Et;
-        finite = finite && isfinite(E[q]);
+        const double Eq = (1 - K.alpha) * Es + K.alpha * Et;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+            if (r == q) E[r] = Eq;
+        finite = finite && isfinite(Eq);
     }
     if (!finite) status |= SFB_ST_NONFINITE;
     return status;
