@@ -41,7 +41,9 @@ EXTRA = {
              (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
              (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False),
              (25, -3, 32, 4, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -3, 32, 4, "imm+r2", False), (28, -3, 32, 4, "imm+r3", False),
-             (29, -3, 32, 3, "imm+r4", False)],
+             (29, -3, 32, 3, "imm+r4", False),
+             (31, -5, 64, 2, "imm", False), (32, -5, 64, 3, "imm", False), (33, -5, 32, 4, "imm", False), (34, -5, 128, 1, "imm", False),
+             (35, -5, 64, 3, "imm+w", False)],
     (4, 0): [(25, -3, 32, 8, "imm", False)], (4, 1): [(25, -3, 32, 8, "imm", False)],
     (6, 0): [(25, -3, 32, 8, "imm", False)], (6, 1): [(25, -3, 32, 6, "imm", False)],
     (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False)],
@@ -145,6 +147,16 @@ def generate(Ls):
                     tab = "#define SFB_LOOP 1\n#define SFB_CH %d\n#define SFB_REDUCED 1\n#define SFB_TNR %d\n" % (ch, TN) + tabsrc
                     skeleton = "sfb_step_kernel.cuh"
                     R_cu, TN_cu, inc_cu = R, 16, "gen/apply_%s.inc" % tag
+                elif R == -5:      # reduced two-lane (re|im) kernel derived from the four-lane form; four-lane fallback on TN/2 nodes
+                    body, tab, meta = emit_step.emit4(L, dd, TN, cm, sync, window, mc, gd, reduced=True)
+                    fbody, ftab, fmeta = emit_step.emit4(L, dd, TN // 2, cm, sync, window, mc, gd)
+                    _write_if_changed(os.path.join(GEN, "apply_%s_full.inc" % tag), fbody)
+                    tab = ('#define SFB_REDUCED 1\n#define SFB_TNR %d\n#define SFB_APPLY_INC_R "gen/apply_%s.inc"\n' % (TN, tag)) + tab
+                    skeleton = "sfb_step_kernel4.cuh"
+                    meta["dfma_node_full"] = fmeta["dfma_node"]
+                    meta["reduced"] = 1
+                    meta["R"] = 1
+                    R_cu, TN_cu, inc_cu = 0, TN // 2, "gen/apply_%s_full.inc" % tag
                 elif R == -3:      # reduced one-lane kernel for real-ODF states (+ in-kernel two-lane fallback, tiles of 16)
                     Rr = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])      # "+rN": warp roles sharing the 32 nodes
                     body, tab, meta = emit_step.emit(L, dd, Rr, TN, cm, False, mc, gd, reduced=True)

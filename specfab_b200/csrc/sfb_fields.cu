@@ -184,7 +184,8 @@ cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const 
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
                            int* status, cudaStream_t st) {
     static int mb = 0;
-    if (!mb) { const char* ev = getenv("SFB_EIJ_MB"); mb = ev ? atoi(ev) : 4;      // 4 CTAs of 128 threads per SM (128 registers, a few spills) beats 2 x 255: the kernel is FP64-latency bound }
+    // 4 CTAs of 128 threads per SM (128 registers, a few spills) beats 2 x 255 registers: the kernel is FP64-latency bound
+    if (!mb) { const char* ev = getenv("SFB_EIJ_MB"); mb = ev ? atoi(ev) : 4; }
     if (N > 0) {
         if (mb == 3) eij_kernel<3><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
         else if (mb == 4) eij_kernel<4><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);

@@ -117,8 +117,14 @@ __device__ __forceinline__ void apply_all(const Ctx& c) {
 
 #include "sfb_step_common.cuh"
 
-__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// the whole step of one tile of kTN nodes starting at node0 (kThreads = 4*kTN threads).  Also the fallback of the reduced
+// two-lane kernel (sfb_step_kernel4r.cuh) for tiles whose states lack the real-ODF symmetry.
+#ifdef SFB_REDUCED
+#define SFB_TILE_FN __device__ __noinline__
+#else
+#define SFB_TILE_FN __device__ __forceinline__
+#endif
+SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsigned char* smem_raw) {
     const int nbuf = P.nstage == 1 ? 1 : (SFB_HORNER ? 2 : 3);
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* forc = bufs + (size_t)nbuf * kNRow * kTN;
@@ -129,7 +135,6 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
     const int sb = lane >> 4;                          // 0: sign set A (m>=0), 1: set B (m<=0)
     const int comp = lane & 1;                         // 0: real part, 1: imaginary part
     const int nl = warp * 8 + ((lane & 15) >> 1);      // node within tile
-    const long long node0 = (long long)blockIdx.x * kTN;
     const int nvalid = (int)min((long long)kTN, P.N - node0);
 
     const uint32_t mb = smem_u32(mbar);
@@ -227,9 +232,22 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepP
         apply_all(c);
         if (!c.last) __syncthreads();
     }
+    __syncthreads();
+    if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");   // full_tile may run again in this CTA
 }
 
+#ifndef SFB_REDUCED
+__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    full_tile(P, (long long)blockIdx.x * kTN, smem_raw);
+}
+#endif
+
 }  // namespace
+
+#ifdef SFB_REDUCED
+#include "sfb_step_kernel4r.cuh"
+#else
 
 extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
     static bool attr_done[64] = {false};
@@ -270,3 +288,4 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     step_kernel<<<(unsigned)ntile, kThreads, smem, st>>>(P);
     return cudaGetLastError();
 }
+#endif  // SFB_REDUCED
