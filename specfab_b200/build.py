@@ -45,10 +45,11 @@ EXTRA = {
              (31, -5, 64, 2, "imm", False), (32, -5, 64, 3, "imm", False), (33, -5, 32, 4, "imm", False), (34, -5, 128, 1, "imm", False),
              (35, -5, 64, 3, "imm+w", False)],
     (4, 0): [(25, -3, 32, 8, "imm", False)], (4, 1): [(25, -3, 32, 8, "imm", False)],
-    (6, 0): [(25, -3, 32, 8, "imm", False)], (6, 1): [(25, -3, 32, 6, "imm", False)],
-    (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False)],
-    (10, 1): [(25, -3, 32, 3, "imm", False), (26, -4, 32, 4, "imm+ch2+r3", False), (27, -4, 32, 4, "imm+ch2+r4", False), (28, -4, 32, 4, "imm+ch2+r2", False)],
-    (12, 0): [(26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
+    (6, 0): [(25, -3, 32, 8, "imm", False), (31, -5, 64, 3, "imm", False)],
+    (6, 1): [(25, -3, 32, 6, "imm", False), (31, -5, 64, 3, "imm", False), (32, -5, 128, 1, "imm", False), (33, -5, 64, 4, "imm", False)],
+    (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (31, -5, 32, 4, "imm+w", False), (32, -5, 64, 2, "imm", False)],
+    (10, 1): [(31, -5, 64, 2, "imm", False), (32, -5, 32, 3, "imm", False), (25, -3, 32, 3, "imm", False), (26, -4, 32, 4, "imm+ch2+r3", False), (27, -4, 32, 4, "imm+ch2+r4", False), (28, -4, 32, 4, "imm+ch2+r2", False)],
+    (12, 0): [(31, -5, 32, 4, "imm+w", False), (32, -5, 32, 3, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
               (1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
     (12, 1): [(26, -4, 32, 3, "imm+ch2+r4", False), (27, -4, 32, 3, "imm+ch2+r2", False), (28, -4, 32, 4, "imm+ch2+r3", False), (25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
               (10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
@@ -66,7 +67,7 @@ EXTRA = {
 TUNE = {
     (4, 0): (-3, 32, 8, "imm", False), (4, 1): (-3, 32, 8, "imm", False),
     (6, 0): (-3, 32, 8, "imm", False), (6, 1): (-3, 32, 6, "imm", False),
-    (8, 0): (-3, 32, 7, "imm", False), (8, 1): (0, 64, 2, "imm", False),
+    (8, 0): (-3, 32, 7, "imm", False), (8, 1): (-5, 64, 3, "imm", False),
     (10, 0): (-3, 32, 5, "imm", False), (10, 1): (-4, 32, 4, "imm+ch2+r3", False),
     (12, 0): (-3, 32, 4, "imm", False), (12, 1): (-4, 32, 4, "imm+ch2+r3", False),
     (14, 0): (-4, 32, 4, "imm+ch2+r4", False), (14, 1): (-4, 32, 3, "imm+ch2+r4", False),
@@ -79,13 +80,13 @@ TUNE = {
 # scheme-specific default: variant 100 (when present) replaces variant 0 for multi-stage (RK4) steps -- with DDRX the
 # classical RK4 keeps three state buffers, which favours the reduced kernel's halved footprint
 TUNE_RK = {
-    (8, 1): (-3, 32, 4, "imm+r3", False),
+    (6, 1): (-5, 64, 3, "imm", False), (8, 1): (-5, 128, 1, "imm", False),
 }
 # the previous full-form defaults stay selectable (variant 40) for comparisons
 FULL_DEFAULT = {
     (4, 0): (1, 16, 8, "imm", False), (4, 1): (1, 16, 8, "imm", False),
     (6, 0): (1, 16, 8, "imm", False), (6, 1): (0, 32, 4, "imm", True),
-    (8, 0): (1, 16, 6, "imm", False), (10, 0): (0, 16, 4, "imm+w", True), (12, 0): (0, 16, 4, "imm+w", True),
+    (8, 0): (1, 16, 6, "imm", False), (8, 1): (0, 64, 2, "imm", False), (10, 0): (0, 16, 4, "imm+w", True), (12, 0): (0, 16, 4, "imm+w", True),
     (10, 1): (-2, 32, 2, "imm+ch2+r4", False), (12, 1): (-2, 32, 2, "imm+ch2+r4", False),
     (14, 0): (-2, 16, 4, "imm+ch2+r4", False), (14, 1): (-2, 16, 3, "imm+ch2+r4", False),
     (16, 0): (-2, 16, 4, "imm+ch2+r6", False), (16, 1): (-2, 16, 3, "imm+ch2+r6", False),

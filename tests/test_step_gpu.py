@@ -204,14 +204,15 @@ def test_reduced_kernel_and_its_fallback(L, terms, scheme):
     if L not in built_L():
         pytest.skip("L=%d not built" % L)
     lm, n = sf.init(L)
-    N = 32 * 5 + 13
+    T = 64                                # covers the 32-node (one-lane) and 64/128-node (two-lane) tiles
+    N = T * 5 + 13
     x = random_states(L, N, 700 + L, True)
     xg = random_states(L, N, 701 + L, False)
-    x[32:64] = xg[32:64]                  # tile 1: general complex states
-    x[70] = xg[70]                        # tile 2: one general node among symmetric ones
-    x[100, 0] += 1e-3j                    # tile 3: Im n_0^0 != 0 only
-    x[130, n - 1] += 1e-9                 # tile 4: one coefficient off its mirror by more than round-off
-    x[140, 3] += 1e-18j                   # tile 4: round-off sized asymmetry (treated as a real ODF)
+    x[T:2 * T] = xg[T:2 * T]              # general complex states
+    x[2 * T + 6] = xg[2 * T + 6]          # one general node among symmetric ones
+    x[3 * T + 36, 0] += 1e-3j             # Im n_0^0 != 0 only
+    x[4 * T + 2, n - 1] += 1e-9           # one coefficient off its mirror by more than round-off
+    x[4 * T + 40, 3] += 1e-18j            # round-off sized asymmetry (treated as a real ODF)
     ug = random_ugrad(N, 702 + L)
     tau = random_tau(N, 703 + L)
     dt = 3.912e-3
@@ -221,7 +222,7 @@ def test_reduced_kernel_and_its_fallback(L, terms, scheme):
     assert relerr_nodes(got, ref).max() < TOL_STEP
     # symmetric nodes stay symmetric bit for bit (so the next step takes the reduced path again)
     idx = {k: j for j, k in enumerate(zip(lm[0].tolist(), lm[1].tolist()))}
-    sym_nodes = [p for p in range(N) if p < 32 or p >= 160]          # tiles 0 and 5 took the reduced path
+    sym_nodes = [p for p in range(N) if p < 32 or p >= 5 * T]        # tiles that certainly took the reduced path
     for (l, m), j in idx.items():
         if m > 0:
             assert np.array_equal(got[sym_nodes, idx[(l, -m)]], (-1) ** m * np.conj(got[sym_nodes, j]))
