@@ -193,7 +193,7 @@ def test_large_field_linearity_property():
     assert relerr_nodes(y1[sel], ref).max() < TOL_STEP
 
 
-@pytest.mark.parametrize("L,terms", [(8, ("lrot", "reg")), (6, ("lrot", "ddrx", "reg")), (10, ("lrot", "reg"))])
+@pytest.mark.parametrize("L,terms", [(8, ("lrot", "reg")), (6, ("lrot", "ddrx", "reg")), (8, ("lrot", "ddrx", "reg")), (10, ("lrot", "reg"))])
 @pytest.mark.parametrize("scheme", ["euler", "rk4"])
 def test_reduced_kernel_and_its_fallback(L, terms, scheme):
     """The default kernels for these (L, terms) compute only the rows m >= 0 when a 32-node tile has the real-ODF
@@ -204,15 +204,16 @@ def test_reduced_kernel_and_its_fallback(L, terms, scheme):
     if L not in built_L():
         pytest.skip("L=%d not built" % L)
     lm, n = sf.init(L)
-    T = 64                                # covers the 32-node (one-lane) and 64/128-node (two-lane) tiles
-    N = T * 5 + 13
+    T = 128                               # largest tile of the reduced kernels (32 one-lane, 64/128 two-lane)
+    N = 4 * T + 13
     x = random_states(L, N, 700 + L, True)
     xg = random_states(L, N, 701 + L, False)
-    x[T:2 * T] = xg[T:2 * T]              # general complex states
-    x[2 * T + 6] = xg[2 * T + 6]          # one general node among symmetric ones
-    x[3 * T + 36, 0] += 1e-3j             # Im n_0^0 != 0 only
-    x[4 * T + 2, n - 1] += 1e-9           # one coefficient off its mirror by more than round-off
-    x[4 * T + 40, 3] += 1e-18j            # round-off sized asymmetry (treated as a real ODF)
+    x[T:T + 40] = xg[T:T + 40]            # general complex states
+    x[T + 70] = xg[T + 70]                # one general node among symmetric ones
+    x[2 * T + 5, 0] += 1e-3j              # Im n_0^0 != 0 only
+    x[2 * T + 50, n - 1] += 1e-9          # one coefficient off its mirror by more than round-off
+    x[2 * T + 100, 3] += 1e-9j
+    x[3 * T + 40, 3] += 1e-18j            # round-off sized asymmetry (treated as a real ODF)
     ug = random_ugrad(N, 702 + L)
     tau = random_tau(N, 703 + L)
     dt = 3.912e-3
@@ -222,7 +223,7 @@ def test_reduced_kernel_and_its_fallback(L, terms, scheme):
     assert relerr_nodes(got, ref).max() < TOL_STEP
     # symmetric nodes stay symmetric bit for bit (so the next step takes the reduced path again)
     idx = {k: j for j, k in enumerate(zip(lm[0].tolist(), lm[1].tolist()))}
-    sym_nodes = [p for p in range(N) if p < 32 or p >= 5 * T]        # tiles that certainly took the reduced path
+    sym_nodes = [p for p in range(N) if p < T or p >= 3 * T]         # tiles that certainly took the reduced path
     for (l, m), j in idx.items():
         if m > 0:
             assert np.array_equal(got[sym_nodes, idx[(l, -m)]], (-1) ** m * np.conj(got[sym_nodes, j]))
