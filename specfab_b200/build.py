@@ -114,9 +114,10 @@ def generate(Ls):
             variants = [(0, R, TN, MINB, cm0, sy0)]
             if (L, dd) in TUNE_RK:
                 variants.append((100,) + TUNE_RK[(L, dd)])
-            if os.environ.get("SFB_EXTRA_VARIANTS", "1") == "1":
-                if (L, dd) in FULL_DEFAULT:
-                    variants.append((40,) + FULL_DEFAULT[(L, dd)])
+            if (L, dd) in FULL_DEFAULT:
+                variants.append((40,) + FULL_DEFAULT[(L, dd)])
+            # the tuning variants of the sweeps in profiles/ are opt-in (SFB_EXTRA_VARIANTS=1): ~100 more translation units
+            if os.environ.get("SFB_EXTRA_VARIANTS", "0") == "1":
                 variants += [v for v in EXTRA.get((L, dd), []) if v[1:] != variants[0][1:]]
             for (vid, R, TN, MINB, cmode, sync) in variants:
                 tag = "L%d_%s" % (L, "ddrx" if dd else "lrot") + ("_v%d" % vid if vid else "")
