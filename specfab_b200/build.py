@@ -36,7 +36,9 @@ EXTRA = {
     (8, 0): [(10, 0, 32, 3, "imm+w", True), (20, -1, 96, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 2, 16, 7, "imm", False), (12, 2, 16, 6, "imm", False), (13, 2, 16, 5, "imm", False), (14, 2, 32, 3, "imm", False),
              (15, 3, 16, 7, "imm", False), (16, 2, 16, 7, "imm+c6", False),
-             (25, -3, 32, 7, "imm+r2", False), (26, -3, 32, 7, "imm+r3", False), (27, -3, 32, 7, "imm+c4", False), (28, -3, 32, 7, "imm+c8", False)],
+             (25, -3, 32, 7, "imm+r2", False), (26, -3, 32, 7, "imm+r3", False), (27, -3, 32, 7, "imm+c4", False), (28, -3, 32, 7, "imm+c8", False),
+             (31, -3, 32, 9, "imm+ip", False), (32, -3, 32, 10, "imm+ip", False), (33, -3, 32, 11, "imm+ip", False), (34, -3, 32, 12, "imm+ip", False),
+             (35, -3, 32, 8, "imm+ip", False)],
     (8, 1): [(1, 1, 32, 3, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r2", False),
              (11, 0, 64, 2, "imm", False), (12, 0, 32, 4, "imm", False), (13, 0, 64, 2, "imm+w", False), (14, 0, 64, 2, "imm+g1500", True),
              (15, 2, 16, 5, "imm", False), (16, 2, 16, 4, "imm", False), (17, 2, 32, 3, "imm", False), (18, 3, 16, 4, "imm", False),
@@ -44,12 +46,13 @@ EXTRA = {
              (29, -3, 32, 3, "imm+r4", False),
              (31, -5, 64, 2, "imm", False), (32, -5, 64, 3, "imm", False), (33, -5, 32, 4, "imm", False), (34, -5, 128, 1, "imm", False),
              (35, -5, 64, 3, "imm+w", False)],
-    (4, 0): [(25, -3, 32, 8, "imm", False)], (4, 1): [(25, -3, 32, 8, "imm", False)],
-    (6, 0): [(25, -3, 32, 8, "imm", False), (31, -5, 64, 3, "imm", False)],
+    (4, 0): [(25, -3, 32, 8, "imm", False), (31, -3, 32, 16, "imm+ip", False), (32, -3, 32, 12, "imm+ip", False)],
+    (4, 1): [(25, -3, 32, 8, "imm", False), (31, -3, 32, 12, "imm+ip", False), (32, -3, 32, 10, "imm+ip", False)],
+    (6, 0): [(25, -3, 32, 8, "imm", False), (31, -3, 32, 16, "imm+ip", False), (32, -3, 32, 12, "imm+ip", False), (33, -3, 32, 14, "imm+ip", False)],
     (6, 1): [(25, -3, 32, 6, "imm", False), (31, -5, 64, 3, "imm", False), (32, -5, 128, 1, "imm", False), (33, -5, 64, 4, "imm", False)],
-    (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (31, -5, 32, 4, "imm+w", False), (32, -5, 64, 2, "imm", False)],
+    (10, 0): [(25, -3, 32, 5, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (31, -3, 32, 9, "imm+ip", False), (32, -3, 32, 8, "imm+ip", False)],
     (10, 1): [(31, -5, 64, 2, "imm", False), (32, -5, 32, 3, "imm", False), (25, -3, 32, 3, "imm", False), (26, -4, 32, 4, "imm+ch2+r3", False), (27, -4, 32, 4, "imm+ch2+r4", False), (28, -4, 32, 4, "imm+ch2+r2", False)],
-    (12, 0): [(31, -5, 32, 4, "imm+w", False), (32, -5, 32, 3, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
+    (12, 0): [(31, -3, 32, 7, "imm+ip", False), (32, -3, 32, 6, "imm+ip", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
               (1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
     (12, 1): [(26, -4, 32, 3, "imm+ch2+r4", False), (27, -4, 32, 3, "imm+ch2+r2", False), (28, -4, 32, 4, "imm+ch2+r3", False), (25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
               (10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
@@ -81,6 +84,9 @@ TUNE = {
 # classical RK4 keeps three state buffers, which favours the reduced kernel's halved footprint
 TUNE_RK = {
     (6, 1): (-5, 64, 3, "imm", False), (8, 1): (-5, 128, 1, "imm", False),
+    # LROT kernels, RK4: in-place stage update (one stage buffer + a register delay queue) -> 12 instead of 7 CTAs per SM at L = 8
+    (4, 0): (-3, 32, 12, "imm+ip", False), (4, 1): (-3, 32, 12, "imm+ip", False), (6, 0): (-3, 32, 16, "imm+ip", False),
+    (8, 0): (-3, 32, 12, "imm+ip", False), (10, 0): (-3, 32, 8, "imm+ip", False), (12, 0): (-3, 32, 6, "imm+ip", False),
 }
 # the previous full-form defaults stay selectable (variant 40) for comparisons
 FULL_DEFAULT = {
@@ -161,8 +167,11 @@ def generate(Ls):
                     R_cu, TN_cu, inc_cu = 0, TN // 2, "gen/apply_%s_full.inc" % tag
                 elif R == -3:      # reduced one-lane kernel for real-ODF states (+ in-kernel two-lane fallback, tiles of 16)
                     Rr = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])      # "+rN": warp roles sharing the 32 nodes
-                    body, tab, meta = emit_step.emit(L, dd, Rr, TN, cm, False, mc, gd, reduced=True)
-                    fbody, _, fmeta = emit_step.emit(L, dd, Rr, 16, cm, False, mc, gd)
+                    ip = "ip" in parts[1:]             # "+ip": in-place stage update (one stage buffer; single role)
+                    body, tab, meta = emit_step.emit(L, dd, Rr, TN, cm, False, mc, gd, reduced=True, inplace=ip)
+                    fbody, _, fmeta = emit_step.emit(L, dd, Rr, 16, cm, False, mc, gd, inplace=ip)
+                    if ip:
+                        tab = "#define SFB_INPLACE 1\n" + tab
                     _write_if_changed(os.path.join(GEN, "apply_%s_full.inc" % tag), fbody)
                     tab = ('#define SFB_REDUCED 1\n#define SFB_TNR %d\n#define SFB_APPLY_INC_R "gen/apply_%s.inc"\n' % (TN, tag)) + tab
                     skeleton = "sfb_step_kernel.cuh"

@@ -55,6 +55,15 @@ struct Ctx {
     bool first, last, isA, valid, ld_n0, ld_acc;
 };
 
+// stage buffers of a multi-stage step: ping-pong pair (+ accumulator for the classical form), or with SFB_INPLACE one
+// buffer updated in place through a register delay queue (codegen/emit_step.py::emit, single role only)
+#ifdef SFB_INPLACE
+constexpr bool kInPlace = true;
+#else
+constexpr bool kInPlace = false;
+#endif
+constexpr int kNBufRK = (kInPlace ? 1 : 2) + (SFB_DDRX ? 1 : 0);
+
 // RK4 formulation: see sfb_step_kernel4.cuh (Horner form of the Taylor polynomial for the linear,
 // DDRX-free kernels; classical k1..k4 with an accumulator buffer when DDRX makes the RHS state dependent).
 #define SFB_HORNER (!SFB_DDRX)
@@ -74,9 +83,10 @@ __device__ __forceinline__ double2 acc_load(const Ctx& c) {
 #endif
     return v;
 }
-// finalize one row, branch-free (selects + predicated stores)
-template <int l, int mu>
-__device__ __forceinline__ void row_out(const Ctx& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
+// finalize one row, branch-free (selects + predicated stores); returns the stage output y.  STORE: write y to the
+// next-stage buffer now; otherwise the caller commits it later (in-place scheme)
+template <int l, int mu, bool STORE>
+__device__ __forceinline__ double2 row_out(const Ctx& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
     double d = fma(c.lam, -(double)(l * (l + 1)), c.c0);
     d = fma(c.rm, c_reg.regdiag[l / 2], d);
     kr = fma(d, zr, kr);
@@ -87,17 +97,26 @@ __device__ __forceinline__ void row_out(const Ctx& c, double kr, double ki, doub
     const long long goff = (long long)hrow(l) * c.ld_out + (long long)mu * c.sld;
 #if SFB_HORNER
     const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
-    if (own && !c.last) (mu == 0 ? c.oz : c.op)[off] = y;
+    if (STORE && own && !c.last) (mu == 0 ? c.oz : c.op)[off] = y;
     if (own && c.last && c.valid) c.gout[goff] = y;
 #else
     const double2 A = make_double2(fma(c.bs, kr, c.first ? zr : acc.x), fma(c.bs, ki, c.first ? zi : acc.y));
     const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
-    if (own && !c.last) { (mu == 0 ? c.oz : c.op)[off] = y; (mu == 0 ? c.az : c.ap)[off] = A; }
+    if (own && !c.last) { if (STORE) (mu == 0 ? c.oz : c.op)[off] = y; (mu == 0 ? c.az : c.ap)[off] = A; }
     if (own && c.last && c.valid) c.gout[goff] = A;
 #endif
+    return y;
+}
+template <int l, int mu>
+__device__ __forceinline__ void row_commit(const Ctx& c, double2 y) {
+    const bool own = (mu != 0) || c.isA;
+    if (own && !c.last) (mu == 0 ? c.oz : c.op)[2 * pslot(l, mu) * kTN] = y;
 }
 #define SFB_ROW_PRE(l, mu, q, r) const double2 q = n0_load<l, mu>(c), r = acc_load<l, mu>(c)
-#define SFB_ROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out<l, mu>(c, ar, ai, zr, zi, q, r)
+#define SFB_ROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out<l, mu, true>(c, ar, ai, zr, zi, q, r)
+#define SFB_ROW_OUTQ(l, mu, ar, ai, zr, zi, q, r, o) o = row_out<l, mu, false>(c, ar, ai, zr, zi, q, r)
+#define SFB_ROW_COMMIT(l, mu, o) row_commit<l, mu>(c, o)
+#define SFB_COMMIT_FENCE() __syncwarp()      // the partner lane set has read the rows that are overwritten next (one-warp CTAs)
 // keeps the warps of a CTA within one instruction-cache window of the generated straight-line code
 #define SFB_LOCKSTEP(lo, hi) __syncthreads()
 
@@ -129,7 +148,7 @@ __device__ __forceinline__ void apply_role(const Ctx& c, int role) {
 #define SFB_TILE_FN __device__ __forceinline__
 #endif
 SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsigned char* smem_raw) {
-    const int nbuf = P.nstage == 1 ? 1 : (SFB_HORNER ? 2 : 3);
+    const int nbuf = P.nstage == 1 ? 1 : kNBufRK;
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* forc = bufs + (size_t)nbuf * kNRow * kTN;
     double* scal = reinterpret_cast<double*>(forc + 2 * kNF * kTN);
@@ -210,7 +229,7 @@ SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsign
 
     for (int s = 0; s < P.nstage; ++s) {
         // n0 is re-read from global (L2) in the later RK stages: inputs 0,1,0,1 ; outputs 1,0,1 ; accumulator 2
-        const int ib = s & 1, ob = (s + 1) & 1;
+        const int ib = kInPlace ? 0 : (s & 1), ob = kInPlace ? 0 : ((s + 1) & 1);
         const double2* yin = bufs + (size_t)ib * kNRow * kTN + nl;
         double2* yout = bufs + (size_t)ob * kNRow * kTN + nl;
         c.yz = yin; c.yp = yin + sb * kTN; c.yn = yin + (1 - sb) * kTN;
@@ -271,7 +290,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     const size_t fixed = (size_t)2 * kNF * kTN * 16 + (size_t)kNSc * kTN * 8 + 16 + kRingBytes;
     const size_t per_buf = (size_t)kNRow * kTN * 16;
     const size_t lim = 227 * 1024;
-    const int nbuf_rk = SFB_HORNER ? 2 : 3;
+    const int nbuf_rk = kNBufRK;
     const size_t smem_max = (nbuf_rk * per_buf + fixed <= lim) ? nbuf_rk * per_buf + fixed : per_buf + fixed;
     cudaError_t e;
     int dev = 0;

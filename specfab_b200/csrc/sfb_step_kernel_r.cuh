@@ -54,8 +54,10 @@ __device__ __forceinline__ double2 acc_load_r(const CtxR& c) {
 #endif
     return v;
 }
-template <int l, int mu>
-__device__ __forceinline__ void row_out_r(const CtxR& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
+// finalize one row; returns the stage output y.  STORE: write y to the next-stage buffer now (two-buffer scheme);
+// otherwise the caller parks it in a register and commits it later (in-place scheme, SFB_INPLACE)
+template <int l, int mu, bool STORE>
+__device__ __forceinline__ double2 row_out_r(const CtxR& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
     double d = fma(c.lam, -(double)(l * (l + 1)), c.c0);
     d = fma(c.rm, c_reg.regdiag[l / 2], d);
     kr = fma(d, zr, kr);
@@ -65,12 +67,12 @@ __device__ __forceinline__ void row_out_r(const CtxR& c, double kr, double ki, d
     const double n0r = c.first ? zr : n0.x, n0i = c.first ? zi : n0.y;
 #if SFB_HORNER
     const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
-    if (!c.last) c.op[off] = y;
+    if (STORE && !c.last) c.op[off] = y;
     const double2 res = y;
 #else
     const double2 A = make_double2(fma(c.bs, kr, c.first ? zr : acc.x), fma(c.bs, ki, c.first ? zi : acc.y));
     const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
-    if (!c.last) { c.op[off] = y; c.ap[off] = A; }
+    if (!c.last) { if (STORE) c.op[off] = y; c.ap[off] = A; }
     const double2 res = A;
 #endif
     if (c.last && c.valid) {
@@ -78,9 +80,12 @@ __device__ __forceinline__ void row_out_r(const CtxR& c, double kr, double ki, d
         if (mu != 0)      // mirror row: (-1)^mu conj
             c.gout[(long long)(hrow(l) - mu) * c.ld_out] = (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y);
     }
+    return y;
 }
 #define SFB_RROW_PRE(l, mu, q, r) const double2 q = n0_load_r<l, mu>(c), r = acc_load_r<l, mu>(c)
-#define SFB_RROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out_r<l, mu>(c, ar, ai, zr, zi, q, r)
+#define SFB_RROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out_r<l, mu, true>(c, ar, ai, zr, zi, q, r)
+#define SFB_RROW_OUTQ(l, mu, ar, ai, zr, zi, q, r, o) o = row_out_r<l, mu, false>(c, ar, ai, zr, zi, q, r)
+#define SFB_RROW_COMMIT(l, mu, o) do { if (!c.last) c.op[pslot(l, mu) * kTNR] = o; } while (0)
 
 #ifdef SFB_LOOP
 #include "sfb_step_loop_r.cuh"
@@ -95,7 +100,7 @@ __device__ __forceinline__ void apply_reduced(const CtxR& c, int role) {
 
 __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbStepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int nbuf = P.nstage == 1 ? 1 : (SFB_HORNER ? 2 : 3);
+    const int nbuf = P.nstage == 1 ? 1 : kNBufRK;
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* forc = bufs + (size_t)nbuf * kNRowR * kTNR;
     double* scal = reinterpret_cast<double*>(forc + kNF * kTNR);
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
     c.ap = bufs + (size_t)(nbuf - 1) * kNRowR * kTNR + t;
 
     for (int s = 0; s < P.nstage; ++s) {
-        const int ib = s & 1, ob = (s + 1) & 1;
+        const int ib = kInPlace ? 0 : (s & 1), ob = kInPlace ? 0 : ((s + 1) & 1);
         c.yp = bufs + (size_t)ib * kNRowR * kTNR + t;
         c.op = bufs + (size_t)ob * kNRowR * kTNR + t;
         c.first = (s == 0);
@@ -265,7 +270,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     static bool attr_done[64] = {false};
     const size_t fixed = (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16 + kRingBytes;
     const size_t per_buf = (size_t)kNRowR * kTNR * 16;
-    const int nbuf_rk = SFB_HORNER ? 2 : 3;
+    const int nbuf_rk = kNBufRK;
     const size_t smem_max = nbuf_rk * per_buf + fixed;
     // the general-path fallback (full_tile, 16 nodes, both row planes, both forcing blocks) uses the same bytes
     static_assert((size_t)kNRow * kTN == (size_t)kNRowR * kTNR && 2 * kNF * kTN == kNF * kTNR, "fallback must fit the reduced layout");

@@ -67,6 +67,12 @@ if __name__ == "__main__":
             run(L, 1_000_000, ("lrot", "reg"), "euler", V)
             run(L, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
             run(L, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
+    if which == "ip":
+        run(4, 1_000_000, ("lrot", "reg"), "rk4", V)
+        run(4, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V)
+        run(6, 1_000_000, ("lrot", "reg"), "rk4", V)
+        run(10, 1_000_000, ("lrot", "reg"), "rk4", V)
+        run(12, 500_000, ("lrot", "reg"), "rk4", V)
     if which == "r4":
         run(6, 1_000_000, ("lrot", "reg"), "rk4", V)
         run(6, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V)
