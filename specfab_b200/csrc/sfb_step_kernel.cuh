@@ -79,7 +79,7 @@ template <int l, int mu>
 __device__ __forceinline__ double2 acc_load(const Ctx& c) {
     double2 v = make_double2(0.0, 0.0);
 #if !SFB_HORNER
-    if (c.ld_acc) v = (mu == 0 ? c.az : c.ap)[2 * pslot(l, mu) * kTN];
+    if (c.ld_acc && (mu != 0 || c.isA)) v = (mu == 0 ? c.az : c.ap)[2 * pslot(l, mu) * kTN];   // set B never owns m = 0 rows
 #endif
     return v;
 }

@@ -71,7 +71,7 @@ __device__ __forceinline__ double acc_load(const Ctx& c) {
     return 0.0;
 #else
     double v = 0.0;
-    if (c.ld_acc) v = (mu == 0 ? c.az : c.ap)[4 * pslot(l, mu) * kTN];
+    if (c.ld_acc && (mu != 0 || c.isA)) v = (mu == 0 ? c.az : c.ap)[4 * pslot(l, mu) * kTN];   // set B never owns m = 0 rows
     return v;
 #endif
 }

@@ -157,7 +157,7 @@ __device__ __forceinline__ void apply_loop(const Ctx& c, int role, int nroles, d
             acc[q] = make_double2(0.0, 0.0);
             if (rowok && c.ld_n0 && (mu != 0 || c.isA)) n0[q] = c.gin[(long long)(l * (l + 1) / 2) * c.ld_in + (long long)mu * c.sld_in];
 #if !SFB_HORNER
-            if (rowok && c.ld_acc) acc[q] = (mu == 0 ? c.az : c.ap)[2 * ((l >> 1) * (l >> 1) + mu) * kTN];
+            if (rowok && c.ld_acc && (mu != 0 || c.isA)) acc[q] = (mu == 0 ? c.az : c.ap)[2 * ((l >> 1) * (l >> 1) + mu) * kTN];   // set B never owns m = 0 rows
 #endif
         }
         delta_sweep<-kDm>(c, tp2, mu, hh, ar, ai, zr, zi);
