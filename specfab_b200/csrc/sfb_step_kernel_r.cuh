@@ -168,11 +168,13 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
     }
 
     // ---- real-ODF symmetry of the input to round-off (NaNs fail the test and take the general path)
+    // (with several roles the degrees l are dealt to the warps; a single warp owns all of them and may have batched the loads)
     bool bad = false;
-    if (warp == 0) {
+    {
         const double tol = kSymTol * fabs(bufs[t].x);
 #pragma unroll
         for (int l = 0; l <= kL; l += 2) {
+            if (kBatchAll ? (warp != 0) : (((l / 2) % kR) != warp)) continue;
             bad |= !(fabs(bufs[(size_t)pslot(l, 0) * kTNR + t].y) <= tol);
             double2 vl[kL > 0 ? kL : 1];
             if (!kBatchAll) {
