@@ -80,6 +80,16 @@ int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t l
                      const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
                      const sfb_step_opts* opts, void* stream);
 
+/* One call per FE time step (SURVEY.md 8b "step_moments_Eij_arr", BASELINE config 5): the fused step above, then on the
+ * new state a2 (optional), a4 (optional), the a2 eigenframe (ei, lami: optional, both or none) and the eigenenhancements
+ * Eij (N,6) in that frame -- what src/specfabpy/fenics/CPO.py:evolve + src/specfabpy/fenics/enhancementfactor.py:101-128 do
+ * per node.  All launches go to `stream` back to back; the state never leaves the device between them.  Any of
+ * a2/a4/ei/lami/status may be NULL.  Device pointers; arrays are packed with leading dimension N except nlm (ld). */
+int sfb_step_moments_Eij_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                                 const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t, const sfb_step_opts* opts,
+                                 const double* Eij_grain, double alpha, int n_grain,
+                                 double* Eij, double* a2, double* a4, double* ei, double* lami, int32_t* status, void* stream);
+
 /* a2(nlm) -> (N,3,3)                         src/specfabpy.f90:583-590, src/moments.f90:37-44 */
 int sfb_a2_arr(const double* nlm, int64_t N, int64_t ld, double* a2);
 int sfb_a2_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a2, void* stream);

@@ -21,7 +21,7 @@ from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, Sp
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
-           "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "Eij_tranisotropic_arr_dev",
+           "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "step_moments_Eij_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
 
 _state = {"L": None, "n": None}
@@ -590,6 +590,39 @@ def step_arr_dev(nlm, ugrad, tau=None, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=
     _lib.check(lib.sfb_step_arr_dev(nlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
                                     tau.data_ptr() if tau is not None else None, N, C.byref(o), _stream_ptr()))
     return out
+
+
+def step_moments_Eij_arr_dev(nlm, ugrad, tau, Eij_grain, alpha, n_grain, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0,
+                             Gamma0=0.0, Lambda=0.0, terms=("lrot", "reg"), scheme="euler", nsteps=1, want_a2=False, want_a4=False,
+                             want_frame=False):
+    """One FE time step on a resident field: fused step, then a2 / a4 / a2 eigenframe / eigenenhancements of the new
+    state (SURVEY 8b step_moments_Eij_arr, BASELINE config 5).  Scalars Gamma0 / Lambda.  Returns a dict with 'nlm',
+    'Eij' (6,N) and, when asked for, 'a2' (3,3,N), 'a4' (3,3,3,3,N), 'ei' (3,3,N), 'lami' (3,N)."""
+    import torch
+    n = _need_init()
+    if nlm.dtype != torch.complex128 or not nlm.is_cuda or not nlm.is_contiguous() or nlm.shape[0] != n:
+        raise ValueError("nlm must be a contiguous CUDA complex128 tensor of shape (nlm_len, N)")
+    N = nlm.shape[1]
+    out = nlm if out is None else out
+    dev = nlm.device
+    res = {"nlm": out, "Eij": torch.empty((6, N), dtype=torch.float64, device=dev)}
+    if want_a2:
+        res["a2"] = torch.empty((3, 3, N), dtype=torch.float64, device=dev)
+    if want_a4:
+        res["a4"] = torch.empty((3, 3, 3, 3, N), dtype=torch.float64, device=dev)
+    if want_frame:
+        res["ei"] = torch.empty((3, 3, N), dtype=torch.float64, device=dev)
+        res["lami"] = torch.empty((3, N), dtype=torch.float64, device=dev)
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    if g.shape != (2,):
+        raise ValueError("Eij_grain must have 2 entries (Emm, Emt)")
+    o = _opts(dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, None, None)
+    ptr = lambda k: res[k].data_ptr() if k in res else None
+    _lib.check(_lib.load().sfb_step_moments_Eij_arr_dev(nlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
+                                                        tau.data_ptr() if tau is not None else None, N, C.byref(o),
+                                                        g.ctypes.data, float(alpha), int(n_grain), res["Eij"].data_ptr(),
+                                                        ptr("a2"), ptr("a4"), ptr("ei"), ptr("lami"), None, _stream_ptr()))
+    return res
 
 
 def a2_arr_dev(nlm, out=None):

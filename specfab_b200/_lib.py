@@ -64,6 +64,8 @@ SIGNATURES = {
     "sfb_M_DDRX_reduced_arr_dev": (C.c_int, [_P, _I64, _P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P]),
     "sfb_ai_to_nlm_arr": (C.c_int, [C.c_int, _P, _I64, _P]),
     "sfb_ai_to_nlm_arr_dev": (C.c_int, [C.c_int, _P, _I64, _I64, _P, _I64, _P]),
+    "sfb_step_moments_Eij_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, C.c_double, C.c_int,
+                                               _P, _P, _P, _P, _P, _P, _P]),
     "sfb_Eij_orthotropic_arr": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P]),
     "sfb_Eij_orthotropic_arr_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
     "sfb_Eij_eigenframe_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P]),

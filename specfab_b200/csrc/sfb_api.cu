@@ -448,6 +448,16 @@ int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const do
     if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }
+int sfb_step_moments_Eij_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                                 const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t, const sfb_step_opts* opts,
+                                 const double* Eij_grain, double alpha, int n_grain,
+                                 double* Eij, double* a2, double* a4, double* ei, double* lami, int32_t* status, void* stream) {
+    int rc = sfb_step_arr_dev(nlm_in, nlm_out, N, ld_in, ld_out, ugrad, ld_u, tau, ld_t, opts, stream);
+    if (rc) return rc;
+    if (a2 && (rc = sfb_a2_arr_dev(nlm_out, N, ld_out, a2, stream))) return rc;
+    if (a4 && (rc = sfb_a4_arr_dev(nlm_out, N, ld_out, a4, stream))) return rc;
+    return sfb_Eij_eigenframe_arr_dev(nlm_out, N, ld_out, Eij_grain, alpha, n_grain, Eij, ei, lami, status, stream);
+}
 int sfb_a6_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a6, void* stream) {
     int rc = basic_check(nlm, N, ld);
     if (rc) return rc;

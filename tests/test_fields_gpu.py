@@ -378,3 +378,25 @@ def test_state_ingest_parity(rank):
     back = getattr(sf, "a%d_to_nlm_arr" % rank)(getattr(sf, "a%d_arr" % rank)(x))
     assert np.abs(back - x[:, :back.shape[1]]).max() < 1e-7
     assert np.array_equal(getattr(sf, "a%d_to_nlm" % rank)(A[3]), got[3])
+
+
+def test_step_moments_Eij_one_call():
+    """step + a2 + a4 + eigenframe + Eij of the new state in one call == the separate calls"""
+    import torch
+    import specfab_b200 as sf
+    sf.init(L)
+    N = 300
+    x = evolved_states(N, 91)
+    ug, tau = random_ugrad(N, 92), random_tau(N, 93)
+    kw = dict(dt=3.912e-3, Gamma0=4.0, terms=("lrot", "ddrx", "reg"), scheme="euler")
+    d = sf.layout_nlm(torch.from_numpy(x).cuda())
+    r = sf.step_moments_Eij_arr_dev(d, sf.layout_mat(torch.from_numpy(ug).cuda()), sf.layout_mat(torch.from_numpy(tau).cuda()),
+                                    GRAIN, ALPHA, 1, out=torch.empty_like(d), want_a2=True, want_a4=True, want_frame=True, **kw)
+    torch.cuda.synchronize()
+    y = sf.step_arr(x, ug, tau, **kw)
+    assert np.array_equal(r["nlm"].cpu().numpy().T, y)
+    E, ei, lami = sf.Eij_eigenframe_arr(y, GRAIN, ALPHA, 1, return_frame=True)
+    assert np.array_equal(r["Eij"].cpu().numpy().T, E)
+    assert np.array_equal(r["lami"].cpu().numpy().T, lami)
+    assert np.array_equal(r["a2"].cpu().numpy().transpose(2, 1, 0), sf.a2_arr(y))
+    assert np.array_equal(r["a4"].cpu().numpy().transpose(4, 3, 2, 1, 0), sf.a4_arr(y))
