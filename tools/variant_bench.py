@@ -1,4 +1,6 @@
-"""Tuning aid: time every compiled kernel variant of (L, terms, scheme) and check it against variant 0."""
+"""Tuning aid: time every compiled kernel variant of (L, terms, scheme) and check it against variant 0.
+The tuning variants (build.py EXTRA) are only compiled with SFB_EXTRA_VARIANTS=1 python -m specfab_b200.build;
+the default build holds variant 0, the RK4 default (100) and the full-form kernel (40)."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
