@@ -1,6 +1,7 @@
 // C ABI of libspecfab_b200.so (declared in include/specfab_b200.h).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -255,7 +256,9 @@ int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
     CK(cudaGetDevice(&dev));
     if (g_stage.dev != dev) { g_stage.release(); g_stage.dev = dev; }
     const int n = g.n;
-    const int64_t chunk = std::min<int64_t>(N, 1 << 16);
+    static int64_t chunk_nodes = 0;      // nodes per pipeline stage (H2D | kernel | D2H on rotating streams); SFB_CHUNK overrides
+    if (!chunk_nodes) { const char* ev = getenv("SFB_CHUNK"); chunk_nodes = ev ? atoll(ev) : (1 << 16); if (chunk_nodes < 1024) chunk_nodes = 1024; }
+    const int64_t chunk = std::min<int64_t>(N, chunk_nodes);
     const bool ddrx = (o->terms & SFB_DDRX) != 0;
     int slot = 0;
     for (int64_t p0 = 0; p0 < N; p0 += chunk, slot = (slot + 1) % Staging::kSlots) {
