@@ -87,3 +87,70 @@ def test_emitted_source_shape():
 def test_operator_mirror_symmetries_hold_for_all_L():
     for L in (4, 6, 8, 10, 12, 14, 16, 18, 20):
         Operators(L)       # asserts the selection rules and exact mirror symmetries of the tables
+
+
+def apply_plans_reduced(L, plans, y, qe, qo, g):
+    """rows m >= 0 of (M_LROT + M_DDRX_src) y from the m >= 0 half of a real-ODF state only, the way the reduced
+    kernels do it (emit_mu(reduced=True), sfb_step_loop_r.cuh): a column block with nu < 0 reads the rows (l_j, |nu|)
+    and its partial sum is conj-mirrored, S = (-1)^nu conj(S')."""
+    f = lane_forcing(qe, qo, g, +1)
+    out = {}
+    for p in plans:
+        acc = {li: 0j for li in p.rows}
+        for (D, nu, used, items) in p.blocks:
+            yv = {lj: y[idx(lj, abs(nu))] for lj in used}          # positive plane only
+            for (fidx, ent) in items:
+                for li, lst in ent.items():
+                    S = sum(c * yv[lj] for lj, c in lst)
+                    if nu < 0:
+                        S = (-1) ** abs(nu) * np.conj(S)
+                    acc[li] += f[fidx] * S
+        for li in p.rows:
+            out[(li, p.mu)] = acc[li]
+    return out
+
+
+@pytest.mark.parametrize("L", [4, 8, 12])
+@pytest.mark.parametrize("ddrx", [0, 1])
+def test_reduced_form_plan_on_real_odf_states(L, ddrx):
+    """the reduced kernels' algebra: M maps real-ODF states onto real-ODF states and its m >= 0 rows follow from the
+    m >= 0 half of the state (csrc/sfb_step_kernel_r.cuh)"""
+    o.init(L)
+    op, plans = es.plan(L, ddrx)
+    y = random_states(L, 1, 7, True)[0]
+    ug, tau = random_ugrad(1, 8)[0], random_tau(1, 9)[0]
+    D, W = (ug + ug.T) / 2, (ug - ug.T) / 2
+    qe, qo = o.quad_rr(D), o.quad_tp(W)
+    g = o.ddrx_weights(tau) if ddrx else np.zeros(15, complex)
+    ref = o.M_LROT(D, W, 1.0, 0.0) @ y + (o.M_DDRX_src(tau) @ y if ddrx else 0)
+    got = apply_plans_reduced(L, plans, y, qe, qo, g)
+    scale = np.abs(ref).max()
+    for (l, m), v in got.items():
+        assert abs(v - ref[idx(l, m)]) < 5e-15 * scale
+        assert abs((-1) ** m * np.conj(v) - ref[idx(l, -m)]) < 5e-15 * scale       # the mirror rows the kernel writes
+        if m == 0:
+            assert abs(v.imag) < 5e-15 * scale
+
+
+@pytest.mark.parametrize("ddrx", [0, 1])
+def test_inplace_stage_update_never_overwrites_a_live_row(ddrx):
+    """in-place RK stages (emit(..., inplace=True)): replay the emitted order of column reads and commits"""
+    L = 8
+    body, _, _ = es.emit(L, ddrx, 1, 32, reduced=True, inplace=True)
+    import re
+    committed = set()
+    rows_read_after_commit = []
+    mu = None
+    for line in body.splitlines():
+        m = re.search(r"canonical mu = (\d+)", line)
+        if m:
+            mu = int(m.group(1))
+        m = re.search(r"SFB_RROW_COMMIT\((\d+), (\d+),", line)
+        if m:
+            committed.add(es.pslot(int(m.group(1)), int(m.group(2))))
+        m = re.search(r"= yp\[(\d+) \* SFB_TNR\]", line)
+        if m and int(m.group(1)) in committed:
+            rows_read_after_commit.append((mu, int(m.group(1))))
+    assert not rows_read_after_commit
+    assert len(committed) == (L // 2 + 1) ** 2          # every row is committed exactly once per stage
+    assert body.count("SFB_RROW_COMMIT(") == len(committed)
