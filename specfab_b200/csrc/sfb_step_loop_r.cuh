@@ -58,8 +58,10 @@ __device__ __forceinline__ void item_r(const double* tp, const double2 f, bool m
     }
 }
 
+// fl: the eight M_LROT forcing entries (qe[-2..2], i*qo[-1..1]) of this lane's node, loaded once per stage and kept in
+// registers (they are needed by every (mu, chunk) item; the 15 DDRX weights stay in shared memory)
 template <int D>
-__device__ __forceinline__ void delta_body_r(const CtxR& c, const double2* tp2, int mu, const int (&hh)[kNY],
+__device__ __forceinline__ void delta_body_r(const CtxR& c, const double2 (&fl)[8], const double2* tp2, int mu, const int (&hh)[kNY],
                                              double (&ar)[kCH], double (&ai)[kCH], double (&zr)[kCH], double (&zi)[kCH]) {
     constexpr int aD = D < 0 ? -D : D;
     constexpr int cnt = body_count<D>();
@@ -80,8 +82,9 @@ __device__ __forceinline__ void delta_body_r(const CtxR& c, const double2* tp2, 
     const bool mir = nu < 0;
     const double sg = (mir && (anu & 1)) ? -1.0 : 1.0;
     const double* t = cf;
-    if (aD <= 2) { item_r<1>(t, c.fz[(D + 2) * kTNR], mir, sg, y, ar, ai); t += 3 * kCH; }                 // A: qe[D]
-    if (aD <= 1) { item_r<0>(t, c.fz[(5 + D + 1) * kTNR], mir, sg, y, ar, ai); t += kCH; }               // B: i*qo[D]
+    // register-resident forcing pays for the LROT kernels (-5..8 %); with DDRX the registers are worth more (+6..14 % slower)
+    if (aD <= 2) { item_r<1>(t, SFB_DDRX ? c.fz[(D + 2) * kTNR] : fl[aD <= 2 ? D + 2 : 0], mir, sg, y, ar, ai); t += 3 * kCH; }           // A: qe[D]
+    if (aD <= 1) { item_r<0>(t, SFB_DDRX ? c.fz[(5 + D + 1) * kTNR] : fl[aD <= 1 ? 5 + D + 1 : 0], mir, sg, y, ar, ai); t += kCH; }       // B: i*qo[D]
 #if SFB_DDRX
     if (D == 0) { item_r<0>(t, c.fz[8 * kTNR], mir, sg, y, ar, ai); t += kCH; }                          // lk = 0
     if (aD <= 2) { item_r<1>(t, c.fz[(8 + 3 + D) * kTNR], mir, sg, y, ar, ai); t += 3 * kCH; }           // lk = 2: k = 3 + D
@@ -90,11 +93,11 @@ __device__ __forceinline__ void delta_body_r(const CtxR& c, const double2* tp2, 
 }
 
 template <int D>
-__device__ __forceinline__ void delta_sweep_r(const CtxR& c, const double2* tp2, int mu, const int (&hh)[kNY],
+__device__ __forceinline__ void delta_sweep_r(const CtxR& c, const double2 (&fl)[8], const double2* tp2, int mu, const int (&hh)[kNY],
                                               double (&ar)[kCH], double (&ai)[kCH], double (&zr)[kCH], double (&zi)[kCH]) {
     if constexpr (D <= kDm) {
-        delta_body_r<D>(c, tp2, mu, hh, ar, ai, zr, zi);
-        delta_sweep_r<D + 1>(c, tp2 + body_count<D>() / 2, mu, hh, ar, ai, zr, zi);
+        delta_body_r<D>(c, fl, tp2, mu, hh, ar, ai, zr, zi);
+        delta_sweep_r<D + 1>(c, fl, tp2 + body_count<D>() / 2, mu, hh, ar, ai, zr, zi);
     }
 }
 
@@ -102,6 +105,9 @@ __device__ __forceinline__ void delta_sweep_r(const CtxR& c, const double2* tp2,
 __device__ __forceinline__ void apply_loop_r(const CtxR& c, int role, int nroles, double2* ring, int lane) {
     int slot = 0;
     if (role < SFB_LT_NITEMS) ring_fetch(ring, c.ktab + (size_t)role * kPairs, lane);
+    double2 fl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fl[i] = SFB_DDRX ? make_double2(0.0, 0.0) : c.fz[i * kTNR];
     for (int it = role; it < SFB_LT_NITEMS; it += nroles) {
         const int nxt = it + nroles;
         if (nxt < SFB_LT_NITEMS) {
@@ -134,7 +140,7 @@ __device__ __forceinline__ void apply_loop_r(const CtxR& c, int role, int nroles
             if (rowok && c.ld_acc) acc[q] = c.ap[((l >> 1) * (l >> 1) + mu) * kTNR];
 #endif
         }
-        delta_sweep_r<-kDm>(c, tp2, mu, hh, ar, ai, zr, zi);
+        delta_sweep_r<-kDm>(c, fl, tp2, mu, hh, ar, ai, zr, zi);
 #pragma unroll
         for (int q = 0; q < kCH; ++q) {
             const int l = kL - 2 * (k * kCH + q);
