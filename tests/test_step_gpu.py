@@ -237,3 +237,36 @@ def test_reduced_kernel_and_its_fallback(L, terms, scheme):
     sf.step_arr_dev(d, dug, dtau, dt=dt, Gamma0=4.0, terms=terms, scheme=scheme, out=d)
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy().T, got)
+
+
+@pytest.mark.parametrize("L,terms", [(8, ("lrot", "reg")), (8, ("lrot", "ddrx", "reg")), (12, ("lrot", "reg")), (12, ("lrot", "ddrx", "reg")),
+                                     (20, ("lrot", "ddrx", "cdrx", "reg"))])
+def test_full_form_kernels_agree_with_the_defaults(L, terms):
+    """variant 40 = the stand-alone full-form kernel of every (L, terms) (build.py FULL_DEFAULT): same results as the
+    default (reduced) kernels on physical states, to round-off, and the same oracle parity on general states"""
+    import specfab_b200 as sf
+    from specfab_b200 import _lib
+    if L not in built_L():
+        pytest.skip("L=%d not built" % L)
+    have = {(k["L"], k["ddrx"], k["variant"]) for k in sf.build_info()["step_kernels"]}
+    if (L, int("ddrx" in terms), 40) not in have:
+        pytest.skip("no separate full-form kernel for this configuration")
+    sf.init(L)
+    N = 150 if L <= 12 else 40
+    ug, tau = random_ugrad(N, 800 + L), random_tau(N, 801 + L)
+    ddrx = "ddrx" in terms
+    kw = dict(dt=3.912e-3, Gamma0=4.0, Lambda=0.1, terms=terms)
+    try:
+        for scheme in ("euler", "rk4"):
+            xs = random_states(L, N, 802 + L, True)
+            _lib.load().sfb_set_variant(0)
+            a = sf.step_arr(xs, ug, tau, scheme=scheme, **kw)
+            _lib.load().sfb_set_variant(40)
+            b = sf.step_arr(xs, ug, tau, scheme=scheme, **kw)
+            assert relerr_nodes(a, b).max() < 1e-14
+        xg = random_states(L, 24, 803 + L, False)
+        got = sf.step_arr(xg, ug[:24], tau[:24], scheme="rk4", **kw)
+        ref = oracle_steps(L, xg, ug[:24], tau[:24], "rk4", 1, dt=3.912e-3, Gamma0=4.0, Lambda=0.1, use_ddrx=ddrx, use_cdrx="cdrx" in terms)
+        assert relerr_nodes(got, ref).max() < TOL_STEP
+    finally:
+        _lib.load().sfb_set_variant(0)
