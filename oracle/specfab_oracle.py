@@ -805,6 +805,30 @@ def Eij_tranisotropic(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_status=
 
 
 # ---------------------------------------------------------------------------------------------
+# discrete (grain-ensemble) lattice rotation, the reference's own cross-check of M_LROT (src/dynamics.f90:112-137)
+# ---------------------------------------------------------------------------------------------
+
+def dri_LROT(ri, D, W, iota):
+    """src/dynamics.f90:112-123: d r_i/dt = (W + iota (r r^T D - D r r^T)) r_i for every grain axis r_i (rows of ri)"""
+    ri = np.asarray(ri, dtype=np.float64)
+    out = np.empty_like(ri)
+    for j, r in enumerate(ri):
+        mm = np.outer(r, r)
+        out[j] = (W + iota * (mm @ D - D @ mm)) @ r
+    return out
+
+
+def ri_LROT(ri0, dt, Nt, D, W, iota):
+    """src/dynamics.f90:125-137: Euler steps with renormalisation; D, W (Nt,3,3); returns (Nt, ngrains, 3)"""
+    ri = np.empty((Nt,) + np.shape(ri0))
+    ri[0] = ri0
+    for i in range(Nt - 1):
+        new = ri[i] + dt * dri_LROT(ri[i], D[i], W[i], iota)
+        ri[i + 1] = new / np.linalg.norm(new, axis=1)[:, None]
+    return ri
+
+
+# ---------------------------------------------------------------------------------------------
 # reduced form (src/reducedform.f90)
 # ---------------------------------------------------------------------------------------------
 
