@@ -91,9 +91,11 @@ __device__ __forceinline__ void eig3_sym(const double m[3][3], double w[3], doub
             const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;
             const double apq = a[p][q];
             if (apq != 0.0) {
-                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                // tan of the rotation angle, t = sgn(theta)/(|theta| + sqrt(theta^2+1)) with theta = (aqq-app)/(2 apq), written
+                // with ONE division and one square root: t = sgn(d) apq / (|d| + sqrt(d^2 + apq^2)), d = (aqq-app)/2
+                const double dlt = 0.5 * (a[q][q] - a[p][p]);
+                const double t = (dlt >= 0 ? apq : -apq) / (fabs(dlt) + sqrt(fma(dlt, dlt, apq * apq)));
+                const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
                 const int k = 3 - p - q;
                 const double akp = a[k][p], akq = a[k][q];
                 a[p][p] -= t * apq;
@@ -207,7 +209,7 @@ __device__ __forceinline__ double dinner22(const double A[3][3], const double B[
 
 // unblocked left-looking Cholesky of the LOWER triangle (LAPACK dpotf2 'L' semantics, which is what
 // dposv of the reference's LAPACK leaves behind on failure: failed pivot stored, info = column)
-__device__ __forceinline__ int potf2_lower(double a[6][6]) {
+__device__ __forceinline__ int potf2_lower(double a[6][6], double* invd = nullptr) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double ajj = a[j][j];
@@ -216,12 +218,15 @@ __device__ __forceinline__ int potf2_lower(double a[6][6]) {
         if (!(ajj > 0.0)) { a[j][j] = ajj; return j + 1; }
         ajj = sqrt(ajj);
         a[j][j] = ajj;
+        // one reciprocal per column instead of a division per entry (<= 1 ulp from LAPACK's x/ajj; the Eij tolerance is 1e-12)
+        const double rj = 1.0 / ajj;
+        if (invd) invd[j] = rj;
 #pragma unroll
         for (int i = 0; i < 6; ++i) if (i > j) {
             double s = a[i][j];
 #pragma unroll
             for (int k = 0; k < 6; ++k) if (k < j) s -= a[i][k] * a[j][k];
-            a[i][j] = s / ajj;
+            a[i][j] = s * rj;
         }
     }
     return 0;
@@ -324,10 +329,8 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
             for (int j = 0; j < 6; ++j)
                 if (j <= i) F[i][j] = P[i][j];
     }
-    const int info = potf2_lower(F);
     double invd[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) invd[i] = 1.0 / F[i][i];
+    const int info = potf2_lower(F, invd);
     const double inv_t_iso = 1.0 / K.t_iso;
     bool finite = true;
 #ifdef SFB_EIJ_ROLLED
