@@ -163,10 +163,11 @@ __device__ __forceinline__ void load_m_ge0(const double2* __restrict__ nlm, long
 
 __device__ __forceinline__ void a2_from(double2 n00, const double2 n2[3], double a[3][3]) {
     double a2v[6];
-    sfb::ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
+    double2 h[3];
+    sfb::ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v, h);
     // src/moments.f90:37-44 returns f_ev_c2 directly (no Mandel round trip): undo the sqrt(2) scaling exactly
-    // by recomputing the off-diagonals from the same expressions
-    const double2 h1 = sfb::cdiv(n2[1], n00), h2 = sfb::cdiv(n2[2], n00);
+    // by forming the off-diagonals from the same quotients
+    const double2 h1 = h[1], h2 = h[2];
     const double s215 = 0.3651483716701107;
     a[0][0] = a2v[0]; a[1][1] = a2v[1]; a[2][2] = a2v[2];
     a[0][1] = a[1][0] = s215 * (-h2.y);

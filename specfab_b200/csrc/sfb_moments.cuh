@@ -23,9 +23,15 @@ __device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
 // Mandel order (11,22,33,sqrt2*23,sqrt2*13,sqrt2*12)   src/mandel.f90:15-24
 #define SFB_SQRT2 1.4142135623730951
 
-// a2 as Mandel 6-vector.  n2: n_2^m for m = 0,1,2 (only m>=0 enters, ev_c2__body.f90:1-17)
-__device__ __forceinline__ void ev_c2_mandel(double2 n00, double2 n20, double2 n21, double2 n22, double a2v[6]) {
-    const double2 h0 = cdiv(n20, n00), h1 = cdiv(n21, n00), h2 = cdiv(n22, n00);   // n2mhat = n2m/n00
+__device__ __forceinline__ double2 cmul2(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// a2 as Mandel 6-vector.  n2: n_2^m for m = 0,1,2 (only m>=0 enters, ev_c2__body.f90:1-17).
+// n2mhat = n2m/n00 is formed with ONE complex reciprocal (3 divisions instead of 9; <= 2 ulp from the reference's divisions);
+// hout (optional) receives the three quotients.
+__device__ __forceinline__ void ev_c2_mandel(double2 n00, double2 n20, double2 n21, double2 n22, double a2v[6], double2* hout = nullptr) {
+    const double2 rinv = cdiv(make_double2(1.0, 0.0), n00);
+    const double2 h0 = cmul2(n20, rinv), h1 = cmul2(n21, rinv), h2 = cmul2(n22, rinv);
+    if (hout) { hout[0] = h0; hout[1] = h1; hout[2] = h2; }
     const double c = 0.5 * 0.816496580927726;      // 0.5d0*sqrt(2.0d0/3)
     const double s215 = 0.3651483716701107;        // sqrt(2/15.0d0)
     const double third = 1.0 / 3.0;
