@@ -45,7 +45,7 @@ EXTRA = {
              (25, -3, 32, 4, "imm", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -3, 32, 4, "imm+r2", False), (28, -3, 32, 4, "imm+r3", False),
              (29, -3, 32, 3, "imm+r4", False),
              (31, -5, 64, 2, "imm", False), (32, -5, 64, 3, "imm", False), (33, -5, 32, 4, "imm", False), (34, -5, 128, 1, "imm", False),
-             (35, -5, 64, 3, "imm+w", False)],
+             (35, -5, 64, 3, "imm+w", False), (36, -5, 64, 4, "imm", False), (37, -5, 32, 6, "imm", False), (38, -5, 32, 8, "imm", False)],
     (4, 0): [(25, -3, 32, 8, "imm", False), (31, -3, 32, 16, "imm+ip", False), (32, -3, 32, 12, "imm+ip", False)],
     (4, 1): [(25, -3, 32, 8, "imm", False), (31, -3, 32, 12, "imm+ip", False), (32, -3, 32, 10, "imm+ip", False)],
     (6, 0): [(25, -3, 32, 8, "imm", False), (31, -3, 32, 16, "imm+ip", False), (32, -3, 32, 12, "imm+ip", False), (33, -3, 32, 14, "imm+ip", False)],
@@ -55,7 +55,7 @@ EXTRA = {
     (12, 0): [(31, -3, 32, 7, "imm+ip", False), (32, -3, 32, 6, "imm+ip", False), (26, -4, 32, 4, "imm+ch2+r2", False), (27, -4, 32, 4, "imm+ch2+r3", False), (2, 2, 16, 4, "imm", False), (3, 4, 16, 4, "imm", False),
               (1, 1, 16, 4, "imm", False), (20, -1, 64, 1, "imm+w", True), (30, -2, 32, 3, "imm+ch2+r4", False)],
     (12, 1): [(26, -4, 32, 3, "imm+ch2+r4", False), (27, -4, 32, 3, "imm+ch2+r2", False), (28, -4, 32, 4, "imm+ch2+r3", False),
-              (32, -4, 32, 4, "imm+ch4+r3", False), (33, -4, 32, 3, "imm+ch4+r4", False), (25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
+              (32, -4, 32, 5, "imm+ch2+r3", False), (33, -4, 32, 4, "imm+ch2+r4", False), (25, -3, 32, 2, "imm", False), (2, 4, 16, 4, "imm", False), (3, 3, 16, 5, "imm", False), (4, 6, 16, 3, "imm", False), (5, 4, 32, 2, "imm", False),
               (10, 0, 32, 2, "imm", True), (20, -1, 80, 1, "imm", True), (30, -2, 16, 5, "imm+ch2+r2", False), (31, -2, 32, 2, "imm+ch4+r4", False)],
     (20, 0): [(26, -4, 32, 3, "imm+ch2+r6", False), (27, -4, 32, 3, "imm+ch2+r4", False), (2, 5, 16, 3, "imm", False), (3, 4, 16, 3, "imm", False), (4, 7, 16, 2, "imm", False),
               (1, 2, 16, 3, "imm", False), (20, -1, 48, 1, "imm", True), (30, -2, 16, 3, "imm+ch4+r6", False)],

@@ -196,6 +196,21 @@ __device__ void prep_ddrx_d(const ForcSrc& S, int t, double* scal) {
 }
 #endif
 
+// <D> of one node (src/dynamics.f90:402-422) with its ingredients (tau, tau.tau, tau:tau) recomputed from the forcing
+// array: 9 loads and ~40 flops per node and stage buy back 13 doubles of shared memory per node (SFB_NO_DSCAL skeletons)
+__device__ __forceinline__ double ddrx_davg(const ForcSrc& S, double2 n00, const double2 n2[3], const double2 n4[5]) {
+    double T[3][3];
+    load_tau(S, T);
+    double sq[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sq[i][j] = T[i][0] * T[0][j] + T[i][1] * T[1][j] + T[i][2] * T[2][j];
+    const double tv[6] = {T[0][0], T[1][1], T[2][2], SFB_SQRT2 * T[1][2], SFB_SQRT2 * T[0][2], SFB_SQRT2 * T[0][1]};
+    const double sv[6] = {sq[0][0], sq[1][1], sq[2][2], SFB_SQRT2 * sq[1][2], SFB_SQRT2 * sq[0][2], SFB_SQRT2 * sq[0][1]};
+    return sfb::ev_D2(n00, n2, n4, tv, sv, sq[0][0] + sq[1][1] + sq[2][2]);
+}
+
 // task dispatch: kThreads >= 2*kTN in both skeletons
 __device__ __forceinline__ void prep_tile(const SfbStepParams& P, long long node0, int nvalid, int tid, double2* forc, double* scal) {
     const int task = tid / kTN, t = tid - task * kTN;
@@ -203,6 +218,9 @@ __device__ __forceinline__ void prep_tile(const SfbStepParams& P, long long node
     const ForcSrc S = global_src(P, node0 + t);
     if (task == 0) prep_lrot(P, S, node0 + t, t, forc, scal);
 #if SFB_DDRX
+#ifdef SFB_NO_DSCAL
+    if (task == 1) prep_ddrx_g(P, S, node0 + t, t, forc, scal);
+#else
     if (kThreads >= 3 * kTN) {
         if (task == 1) prep_ddrx_g(P, S, node0 + t, t, forc, scal);
         if (task == 2) prep_ddrx_d(S, t, scal);
@@ -210,5 +228,6 @@ __device__ __forceinline__ void prep_tile(const SfbStepParams& P, long long node
         prep_ddrx_g(P, S, node0 + t, t, forc, scal);
         prep_ddrx_d(S, t, scal);
     }
+#endif
 #endif
 }

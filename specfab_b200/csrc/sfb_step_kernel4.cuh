@@ -26,7 +26,8 @@ constexpr int kNRow = 2 * (kL / 2 + 1) * (kL / 2 + 1);   // physical rows: plane
 constexpr int kTN = SFB_TN;
 constexpr int kThreads = 4 * kTN;
 constexpr int kNF = SFB_DDRX ? 23 : 8;                    // forcing entries per lane set
-constexpr int kNSc = SFB_DDRX ? 17 : 4;                   // per-node scalars
+#define SFB_NO_DSCAL 1                                   // <D> ingredients are recomputed per stage, not kept in shared memory
+constexpr int kNSc = 4;                                   // per-node scalars (SC_C0, SC_LAM, SC_RM, SC_G0)
 static_assert(kTN % 8 == 0, "tile must be a multiple of 8 nodes (one warp)");
 
 __constant__ SfbRegConst c_reg;
@@ -220,10 +221,7 @@ SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsign
             for (int m = 0; m < 3; ++m) n2[m] = y[2 * pslot(2, m) * kTN];
 #pragma unroll
             for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[2 * pslot(4, m) * kTN] : make_double2(0.0, 0.0);
-            double tv[6], sv[6];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) { tv[p] = scal[(SC_TAUV + p) * kTN + tid]; sv[p] = scal[(SC_TSQV + p) * kTN + tid]; }
-            const double davg = sfb::ev_D2(y[0], n2, n4, tv, sv, scal[SC_NORM * kTN + tid]);
+            const double davg = ddrx_davg(global_src(P, node0 + tid), y[0], n2, n4);
             scal[SC_C0 * kTN + tid] = -(scal[SC_G0 * kTN + tid] * davg);
         }
         __syncthreads();

@@ -121,15 +121,14 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
     }
-    // ---- per-node forcing (sign set A only): tasks dealt to the first 3*kTNR threads (kThreads = 2*kTNR: tasks 0,1 then 2)
-    for (int w = tid; w < 3 * kTNR; w += kThreads) {
+    // ---- per-node forcing (sign set A only): two tasks per node, one thread each (kThreads = 2*kTNR)
+    for (int w = tid; w < 2 * kTNR; w += kThreads) {
         const int task = w / kTNR, t = w - task * kTNR;
         if (t < nvalid) {
             const ForcSrc S = global_src(P, node0 + t);
             if (task == 0) prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal);
 #if SFB_DDRX
             if (task == 1) prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
-            if (task == 2) prep_ddrx_d<kTNR>(S, t, scal);
 #endif
         }
     }
@@ -214,10 +213,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
             for (int m = 0; m < 3; ++m) n2[m] = y[pslot(2, m) * kTNR];
 #pragma unroll
             for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[pslot(4, m) * kTNR] : make_double2(0.0, 0.0);
-            double tv[6], sv[6];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) { tv[p] = scal[(SC_TAUV + p) * kTNR + tid]; sv[p] = scal[(SC_TSQV + p) * kTNR + tid]; }
-            const double davg = sfb::ev_D2(y[0], n2, n4, tv, sv, scal[SC_NORM * kTNR + tid]);
+            const double davg = ddrx_davg(global_src(P, node0 + tid), y[0], n2, n4);
             scal[SC_C0 * kTNR + tid] = -(scal[SC_G0 * kTNR + tid] * davg);
         }
         __syncthreads();

@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
         if (warp == 0) prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal);
 #if SFB_DDRX
         if (warp == (kR > 1 ? 1 : 0)) prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
-        if (warp == (kR > 2 ? 2 : 0)) prep_ddrx_d<kTNR>(S, t, scal);
 #endif
     }
     {   // wait for the tile
@@ -247,10 +246,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
                 for (int m = 0; m < 3; ++m) n2[m] = y[pslot(2, m) * kTNR];
 #pragma unroll
                 for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[pslot(4, m) * kTNR] : make_double2(0.0, 0.0);
-                double tv[6], sv[6];
-#pragma unroll
-                for (int p = 0; p < 6; ++p) { tv[p] = scal[(SC_TAUV + p) * kTNR + t]; sv[p] = scal[(SC_TSQV + p) * kTNR + t]; }
-                const double davg = sfb::ev_D2(y[0], n2, n4, tv, sv, scal[SC_NORM * kTNR + t]);
+                const double davg = ddrx_davg(global_src(P, node0 + t), y[0], n2, n4);
                 c.c0 = -(scal[SC_G0 * kTNR + t] * davg);
                 if (kR > 1) scal[SC_C0 * kTNR + t] = c.c0;
             }
