@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
-__all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
+__all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "dndt_LATROT", "dndt_DDRX", "dndt_CDRX", "dndt_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
            "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "step_moments_Eij_arr_dev", "Eij_tranisotropic_arr_dev",
@@ -248,6 +248,13 @@ def M_CDRX(nlm):
 def M_REG(nlm, eps):
     """reference: src/specfabpy.f90:237-245"""
     return np.ascontiguousarray(M_REG_arr(np.asarray(eps)[None])[0])
+
+
+# names of older specfab releases for the same operators (BASELINE.json north_star; SURVEY.md naming note)
+dndt_LATROT = M_LROT
+dndt_DDRX = M_DDRX
+dndt_CDRX = M_CDRX
+dndt_REG = M_REG
 
 
 def nlm_LROT(nlm0, dt, Nt, D, W, iota):
