@@ -62,6 +62,13 @@ EXTRA = {
     (20, 1): [(26, -4, 32, 2, "imm+ch2+r6", False), (27, -4, 32, 2, "imm+ch2+r4", False), (28, -4, 32, 2, "imm+ch2+r8", False), (2, 8, 16, 2, "imm", False), (3, 6, 16, 2, "imm", False), (4, 4, 16, 2, "imm", False), (5, 10, 16, 2, "imm", False),
               (1, 2, 16, 2, "imm", False), (20, -1, 32, 1, "imm", True), (30, -2, 16, 2, "imm+ch4+r6", False), (31, -2, 16, 2, "imm+ch2+r8", False)],
 }
+# variants under test (SFB_EXP_VARIANTS=1)
+EXP = {
+    (12, 1): [(131, -4, 32, 4, "imm+ch4+r3", False), (132, -4, 32, 3, "imm+ch4+r3", False), (133, -4, 32, 3, "imm+ch4+r4", False),
+              (135, -4, 32, 4, "imm+ch4+r2", False)],
+    (20, 1): [(131, -4, 32, 2, "imm+ch4+r6", False), (132, -4, 32, 2, "imm+ch4+r4", False),
+              (134, -4, 32, 2, "imm+ch4+r8", False)],
+}
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
 #   DDRX kernels up to L = 8 prefer four lanes per node;  L >= 12 with DDRX and every L >= 14: the table-driven loop kernel
@@ -69,25 +76,30 @@ EXTRA = {
 #   R = -3: reduced one-lane kernel (real-ODF symmetry detected per tile, in-kernel two-lane fallback for general complex
 #   states): half the arithmetic and shared memory per node; 1.2-1.9x the node rate wherever the straight-line form is used.
 TUNE = {
-    (4, 0): (-3, 32, 8, "imm", False), (4, 1): (-3, 32, 8, "imm", False),
-    (6, 0): (-3, 32, 8, "imm", False), (6, 1): (-3, 32, 6, "imm", False),
-    (8, 0): (-3, 32, 7, "imm", False), (8, 1): (-5, 64, 3, "imm", False),
-    (10, 0): (-3, 32, 5, "imm", False), (10, 1): (-4, 32, 4, "imm+ch2+r3", False),
-    (12, 0): (-3, 32, 4, "imm", False), (12, 1): (-4, 32, 4, "imm+ch2+r3", False),
+    (4, 0): (-3, 32, 8, "imm", False), (4, 1): (-3, 32, 6, "imm+ip+a32+cw2", False),
+    (6, 0): (-3, 32, 8, "imm+a32", False), (6, 1): (-3, 32, 3, "imm+a32+cw2", False),
+    (8, 0): (-3, 32, 7, "imm+a32", False), (8, 1): (-5, 64, 3, "imm+a32", False),
+    (10, 0): (-3, 32, 5, "imm+a32", False), (10, 1): (-4, 32, 4, "imm+ch2+r3", False),
+    (12, 0): (-3, 32, 4, "imm+a32", False), (12, 1): (-4, 32, 4, "imm+ch2+r3", False),
     (14, 0): (-4, 32, 4, "imm+ch2+r4", False), (14, 1): (-4, 32, 3, "imm+ch2+r4", False),
     (16, 0): (-4, 32, 4, "imm+ch2+r4", False), (16, 1): (-4, 32, 3, "imm+ch2+r6", False),
     (18, 0): (-4, 32, 3, "imm+ch2+r4", False), (18, 1): (-4, 32, 2, "imm+ch2+r6", False),
     (20, 0): (-4, 32, 3, "imm+ch2+r4", False), (20, 1): (-4, 32, 2, "imm+ch2+r6", False),
 }
+# flags of the reduced one-lane kernel (sweep: profiles/r01_variants_sweep_a32.txt):
+#   "+a32": 32-bit row strides (one multiply-add per global row address) and explicit LDG/STG in the row finalisation;
+#   "+n0" (Horner RK4): n0 re-read from global in every stage -- no selects, zero-initialisation or branches around the loads;
+#   "+cwN": N independent one-warp tiles per CTA (they start together and share the instruction stream's cache misses);
+#   "+ip": in-place RK4 stages (one stage buffer + register delay queue).
 
 
 # scheme-specific default: variant 100 (when present) replaces variant 0 for multi-stage (RK4) steps -- with DDRX the
 # classical RK4 keeps three state buffers, which favours the reduced kernel's halved footprint
 TUNE_RK = {
-    (6, 1): (-5, 64, 3, "imm", False), (8, 1): (-5, 128, 1, "imm", False),
-    # LROT kernels, RK4: in-place stage update (one stage buffer + a register delay queue) -> 12 instead of 7 CTAs per SM at L = 8
-    (4, 0): (-3, 32, 12, "imm+ip", False), (4, 1): (-3, 32, 12, "imm+ip", False), (6, 0): (-3, 32, 16, "imm+ip", False),
-    (8, 0): (-3, 32, 12, "imm+ip", False), (10, 0): (-3, 32, 8, "imm+ip", False), (12, 0): (-3, 32, 6, "imm+ip", False),
+    (6, 1): (-5, 64, 3, "imm", False), (8, 1): (-5, 128, 1, "imm+a32", False),
+    # LROT kernels, RK4: in-place stage update (one stage buffer + a register delay queue) -> 12 instead of 7 warps per SM at L = 8
+    (4, 0): (-3, 32, 12, "imm+ip+a32+n0", False), (4, 1): (-3, 32, 8, "imm+a32", False), (6, 0): (-3, 32, 8, "imm+ip+a32+n0+cw2", False),
+    (8, 0): (-3, 32, 6, "imm+ip+a32+n0+cw2", False), (10, 0): (-3, 32, 4, "imm+ip+a32+n0+cw2", False), (12, 0): (-3, 32, 6, "imm+ip+a32+n0", False),
 }
 # the previous full-form defaults stay selectable (variant 40) for comparisons
 FULL_DEFAULT = {
@@ -126,6 +138,8 @@ def generate(Ls):
             # the tuning variants of the sweeps in profiles/ are opt-in (SFB_EXTRA_VARIANTS=1): ~100 more translation units
             if os.environ.get("SFB_EXTRA_VARIANTS", "0") == "1":
                 variants += [v for v in EXTRA.get((L, dd), []) if v[1:] != variants[0][1:]]
+            if os.environ.get("SFB_EXP_VARIANTS", "0") == "1":     # variants under test in the current tuning session
+                variants += EXP.get((L, dd), [])
             for (vid, R, TN, MINB, cmode, sync) in variants:
                 tag = "L%d_%s" % (L, "ddrx" if dd else "lrot") + ("_v%d" % vid if vid else "")
                 # const_mode string: "imm" | "cbank", optional flags "+w" (register window), "+cN" (>= N DFMA
@@ -133,7 +147,7 @@ def generate(Ls):
                 parts = cmode.split("+")
                 cm = parts[0]
                 window = "w" in parts[1:]
-                mc = max([int(x[1:]) for x in parts[1:] if x.startswith("c") and not x.startswith("ch")] + [1])
+                mc = max([int(x[1:]) for x in parts[1:] if x.startswith("c") and not x.startswith(("ch", "cw"))] + [1])
                 gd = max([int(x[1:]) for x in parts[1:] if x.startswith("g")] + [0])
                 if R == -2:      # table-driven loop kernel (two lanes per node); MINB field = CTAs/SM, "chN" = rows per chunk
                     ch = max([int(x[2:]) for x in parts[1:] if x.startswith("ch")] + [2])
@@ -161,6 +175,8 @@ def generate(Ls):
                     fbody, ftab, fmeta = emit_step.emit4(L, dd, TN // 2, cm, sync, window, mc, gd)
                     _write_if_changed(os.path.join(GEN, "apply_%s_full.inc" % tag), fbody)
                     tab = ('#define SFB_REDUCED 1\n#define SFB_TNR %d\n#define SFB_APPLY_INC_R "gen/apply_%s.inc"\n' % (TN, tag)) + tab
+                    if "a32" in parts[1:]:
+                        tab = "#define SFB_A32 1\n" + tab
                     skeleton = "sfb_step_kernel4.cuh"
                     meta["dfma_node_full"] = fmeta["dfma_node"]
                     meta["reduced"] = 1
@@ -169,10 +185,20 @@ def generate(Ls):
                 elif R == -3:      # reduced one-lane kernel for real-ODF states (+ in-kernel two-lane fallback, tiles of 16)
                     Rr = max([int(x[1:]) for x in parts[1:] if x.startswith("r")] + [1])      # "+rN": warp roles sharing the 32 nodes
                     ip = "ip" in parts[1:]             # "+ip": in-place stage update (one stage buffer; single role)
-                    body, tab, meta = emit_step.emit(L, dd, Rr, TN, cm, False, mc, gd, reduced=True, inplace=ip)
+                    ls = "ls" in parts[1:]             # "+ls" (with "+cwN"): the CTA's tiles run the reduced body in lock step
+                    body, tab, meta = emit_step.emit(L, dd, Rr, TN, cm, ls, mc, gd, reduced=True, inplace=ip)
+                    if ls:
+                        tab = "#define SFB_LS 1\n" + tab
                     fbody, _, fmeta = emit_step.emit(L, dd, Rr, 16, cm, False, mc, gd, inplace=ip)
                     if ip:
                         tab = "#define SFB_INPLACE 1\n" + tab
+                    cw = max([int(x[2:]) for x in parts[1:] if x.startswith("cw")] + [1])
+                    if cw > 1:                     # "+cwN": N independent one-warp tiles per CTA (MINB then counts CTAs of N warps)
+                        tab = "#define SFB_CW %d\n" % cw + tab
+                    if "n0" in parts[1:]:          # "+n0": n0 loaded from global in every stage (Horner kernels), no selects
+                        tab = "#define SFB_N0ALL_REQ 1\n" + tab
+                    if "a32" in parts[1:]:         # "+a32": 32-bit row strides + explicit global loads/stores in the row finalisation
+                        tab = "#define SFB_A32 1\n" + tab
                     _write_if_changed(os.path.join(GEN, "apply_%s_full.inc" % tag), fbody)
                     tab = ('#define SFB_REDUCED 1\n#define SFB_TNR %d\n#define SFB_APPLY_INC_R "gen/apply_%s.inc"\n' % (TN, tag)) + tab
                     skeleton = "sfb_step_kernel.cuh"

@@ -31,6 +31,15 @@ constexpr int kNF = SFB_DDRX ? 23 : 8;                    // forcing entries per
 #define SFB_NO_DSCAL 1                                   // <D> ingredients are recomputed per stage, not kept in shared memory
 constexpr int kNSc = 4;                                   // per-node scalars (SC_C0, SC_LAM, SC_RM, SC_G0)
 static_assert(kTN % 16 == 0, "tile must be a multiple of 16 nodes");
+// SFB_CW > 1 (reduced one-lane kernel, one role): a CTA holds SFB_CW independent one-warp tiles -- warps that start
+// together and run the same instruction stream share its instruction-cache misses.  Every tile-level barrier is then a
+// warp barrier and every tile has its own slice of the dynamic shared memory.
+#ifndef SFB_CW
+#define SFB_CW 1
+#endif
+constexpr int kCW = SFB_CW;
+static_assert(kCW == 1 || kThreads == 32, "several tiles per CTA: one-warp tiles only");
+#define SFB_TILE_SYNC() do { if (kCW > 1) __syncwarp(); else __syncthreads(); } while (0)
 
 __constant__ SfbRegConst c_reg;
 
@@ -156,7 +165,7 @@ SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsign
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(scal + kNSc * kTN);
     double2* rings = reinterpret_cast<double2*>(mbar + 2);          // loop mode: [warps][2][pairs per item]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x % kThreads, warp = tid >> 5, lane = tid & 31;
     const int group = warp / kR, role = warp % kR;
     const int sb = lane >> 4;                       // 0: lane set A (m>=0), 1: lane set B (m<=0)
     const int nl = group * 16 + (lane & 15);        // node within tile
@@ -168,7 +177,7 @@ SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsign
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    SFB_TILE_SYNC();
     if (warp == 0) {
         const uint32_t bytes = (uint32_t)nvalid * 16u;
         if (lane == 0)
@@ -200,7 +209,7 @@ SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsign
                          : "=r"(done) : "r"(mb) : "memory");
         }
     }
-    __syncthreads();
+    SFB_TILE_SYNC();
 
     Ctx c;
     c.isA = (sb == 0);
@@ -260,13 +269,13 @@ SFB_TILE_FN void full_tile(const SfbStepParams& P, const long long node0, unsign
             const double davg = ddrx_davg(global_src(P, node0 + tid), y[0], n2, n4);
             scal[SC_C0 * kTN + tid] = -(scal[SC_G0 * kTN + tid] * davg);
         }
-        __syncthreads();
+        SFB_TILE_SYNC();
         c.c0 = scal[SC_C0 * kTN + nl];
 #endif
         apply_role(c, role);
-        if (!c.last) __syncthreads();
+        if (!c.last) SFB_TILE_SYNC();
     }
-    __syncthreads();
+    SFB_TILE_SYNC();
     if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");   // full_tile may run again in this CTA
 }
 

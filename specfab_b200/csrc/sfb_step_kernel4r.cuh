@@ -24,6 +24,7 @@ struct CtxR {
     double* gout;                     // global output: component of node
     const double* gin;
     long long ld_out, ld_in;
+    unsigned ldo32, ldi32;            // SFB_A32: the same strides as 32-bit values
     double c0, lam, rm;
     double as, bs;
     double sigma;                     // -1 (re lane) / +1 (im lane): sign of the partner's contribution
@@ -31,10 +32,37 @@ struct CtxR {
     bool first, last, valid, ld_n0, ld_acc, isim;
 };
 
+// global row addresses of the row finalisation (see sfb_step_kernel_r.cuh): SFB_A32 = one 32x32->64 multiply-add per
+// address (the launcher rejects ld >= 2^32) and explicit global-space accesses
+#ifdef SFB_A32
+__device__ __forceinline__ unsigned long long mad_wide(unsigned a, unsigned b, unsigned long long c) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+template <int row>
+__device__ __forceinline__ const double* grow_in(const CtxR& c) {
+    return reinterpret_cast<const double*>(mad_wide(c.ldi32, 16u * row, reinterpret_cast<unsigned long long>(c.gin)));
+}
+template <int row>
+__device__ __forceinline__ double* grow_out(const CtxR& c) {
+    return reinterpret_cast<double*>(mad_wide(c.ldo32, 16u * row, reinterpret_cast<unsigned long long>(c.gout)));
+}
+__device__ __forceinline__ double gload(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ void gstore(double* p, double v) { __stcs(p, v); }
+#else
+template <int row>
+__device__ __forceinline__ const double* grow_in(const CtxR& c) { return c.gin + 2 * ((long long)row * c.ld_in); }
+template <int row>
+__device__ __forceinline__ double* grow_out(const CtxR& c) { return c.gout + 2 * ((long long)row * c.ld_out); }
+__device__ __forceinline__ double gload(const double* p) { return *p; }
+__device__ __forceinline__ void gstore(double* p, double v) { *p = v; }
+#endif
+
 template <int l, int mu>
 __device__ __forceinline__ double n0_load_r(const CtxR& c) {
     double v = 0.0;
-    if (c.ld_n0) v = c.gin[2 * ((long long)(hrow(l) + mu) * c.ld_in)];
+    if (c.ld_n0) v = gload(grow_in<hrow(l) + mu>(c));
     return v;
 }
 template <int l, int mu>
@@ -68,9 +96,9 @@ __device__ __forceinline__ void row_out_r(const CtxR& c, double mine, double the
     const double res = A;
 #endif
     if (c.last && c.valid) {
-        c.gout[2 * ((long long)(hrow(l) + mu) * c.ld_out)] = res;
+        gstore(grow_out<hrow(l) + mu>(c), res);
         // mirror row (-1)^mu conj: the re lane keeps the parity sign, the im lane gets the opposite one
-        if (mu != 0) c.gout[2 * ((long long)(hrow(l) - mu) * c.ld_out)] = ((mu & 1) != 0) == c.isim ? res : -res;
+        if (mu != 0) gstore(grow_out<hrow(l) - mu>(c), ((mu & 1) != 0) == c.isim ? res : -res);
     }
 }
 #define SFB_RROW_OUT4(l, mu, m, t, z, q, r) row_out_r<l, mu>(c, m, t, z, q, r)
@@ -181,6 +209,8 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
     c.c0 = 0.0;
     c.ld_out = P.ld_out;
     c.ld_in = P.ld_in;
+    c.ldo32 = (unsigned)P.ld_out;
+    c.ldi32 = (unsigned)P.ld_in;
     c.gout = reinterpret_cast<double*>(P.nlm_out + node0 + nl) + comp;
     c.gin = reinterpret_cast<const double*>(P.nlm_in + node0 + nl) + comp;
     double* wbuf = reinterpret_cast<double*>(bufs) + 2 * nl + comp;
@@ -234,6 +264,9 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     const size_t smem_max = nbuf_rk * per_buf + fixed;
     static_assert((size_t)kNRow * kTN == (size_t)kNRowR * kTNR && 2 * kNF * kTN == kNF * kTNR, "fallback must fit the reduced layout");
     if (smem_max > 227 * 1024) return cudaErrorInvalidConfiguration;
+#ifdef SFB_A32
+    if (Pin.ld_in >= (1LL << 32) || Pin.ld_out >= (1LL << 32)) return cudaErrorInvalidValue;   // 32-bit row strides
+#endif
     cudaError_t e;
     int dev = 0;
     cudaGetDevice(&dev);

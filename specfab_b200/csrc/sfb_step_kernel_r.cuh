@@ -18,6 +18,13 @@
 namespace {
 
 constexpr int kTNR = SFB_TNR;
+// SFB_N0ALL (Horner kernels): n0 is loaded from global in EVERY stage -- no select between the stage input and the loaded
+// value, no zero initialisation, no branch around the loads; stage 0 pays 16 B per row of L2 (not DRAM) traffic for it
+#if defined(SFB_N0ALL_REQ) && SFB_HORNER
+#define SFB_N0ALL 1
+#else
+#define SFB_N0ALL 0
+#endif
 constexpr double kSymTol = 0x1p-46;
 constexpr int kNRowR = (kL / 2 + 1) * (kL / 2 + 1);       // rows (l, m >= 0)
 // one lane per node; kR warp roles share the 32 nodes of the tile (straight-line form: kR = 1, no barriers at all;
@@ -35,16 +42,49 @@ struct CtxR {
     double2* gout;                    // global output, offset by node
     const double2* gin;
     long long ld_out, ld_in;
+    unsigned ldo32, ldi32;            // SFB_A32: the same strides as 32-bit values
     double c0, lam, rm;
     double as, bs;
     bool first, last, valid, ld_n0, ld_acc;
 };
 
+// Global row addresses of the row finalisation.  SFB_A32: base + (16 * row) * ld as ONE 32x32->64 multiply-add
+// (IMAD.WIDE.U32; the launcher rejects ld >= 2^32) and explicit global-space accesses (LDG/STG, L2-only loads, streaming
+// stores) instead of a 64-bit multiply (4-5 integer instructions per address) and generic LD/ST.
+#ifdef SFB_A32
+__device__ __forceinline__ unsigned long long mad_wide(unsigned a, unsigned b, unsigned long long c) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));     // opaque to the optimiser: stays one instruction
+    return r;
+}
+template <int row>
+__device__ __forceinline__ const double2* grow_in(const CtxR& c) {
+    return reinterpret_cast<const double2*>(mad_wide(c.ldi32, 16u * row, reinterpret_cast<unsigned long long>(c.gin)));
+}
+template <int row>
+__device__ __forceinline__ double2* grow_out(const CtxR& c) {
+    return reinterpret_cast<double2*>(mad_wide(c.ldo32, 16u * row, reinterpret_cast<unsigned long long>(c.gout)));
+}
+__device__ __forceinline__ double2 gload(const double2* p) { return __ldcg(p); }
+__device__ __forceinline__ void gstore(double2* p, double2 v) { __stcs(p, v); }
+#else
+template <int row>
+__device__ __forceinline__ const double2* grow_in(const CtxR& c) { return c.gin + (long long)row * c.ld_in; }
+template <int row>
+__device__ __forceinline__ double2* grow_out(const CtxR& c) { return c.gout + (long long)row * c.ld_out; }
+__device__ __forceinline__ double2 gload(const double2* p) { return *p; }
+__device__ __forceinline__ void gstore(double2* p, double2 v) { *p = v; }
+#endif
+
 template <int l, int mu>
 __device__ __forceinline__ double2 n0_load_r(const CtxR& c) {
+#if SFB_N0ALL
+    return gload(grow_in<hrow(l) + mu>(c));      // every stage, every lane (c.gin of a lane beyond N points at the tile's first node)
+#else
     double2 v = make_double2(0.0, 0.0);
-    if (c.ld_n0) v = c.gin[(long long)(hrow(l) + mu) * c.ld_in];
+    if (c.ld_n0) v = gload(grow_in<hrow(l) + mu>(c));
     return v;
+#endif
 }
 template <int l, int mu>
 __device__ __forceinline__ double2 acc_load_r(const CtxR& c) {
@@ -64,7 +104,11 @@ __device__ __forceinline__ double2 row_out_r(const CtxR& c, double kr, double ki
     ki = fma(d, zi, ki);
     if (mu == 0) { ki = 0.0; zi = 0.0; n0.y = 0.0; acc.y = 0.0; }     // n_l^0 of a real ODF is real: drop the round-off
     constexpr int off = pslot(l, mu) * kTNR;
+#if SFB_N0ALL
+    const double n0r = n0.x, n0i = n0.y;         // stage 0 re-reads the rows the bulk copies have just pulled through L2
+#else
     const double n0r = c.first ? zr : n0.x, n0i = c.first ? zi : n0.y;
+#endif
 #if SFB_HORNER
     const double2 y = make_double2(fma(c.as, kr, n0r), fma(c.as, ki, n0i));
     if (STORE && !c.last) c.op[off] = y;
@@ -76,9 +120,9 @@ __device__ __forceinline__ double2 row_out_r(const CtxR& c, double kr, double ki
     const double2 res = A;
 #endif
     if (c.last && c.valid) {
-        c.gout[(long long)(hrow(l) + mu) * c.ld_out] = res;
+        gstore(grow_out<hrow(l) + mu>(c), res);
         if (mu != 0)      // mirror row: (-1)^mu conj
-            c.gout[(long long)(hrow(l) - mu) * c.ld_out] = (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y);
+            gstore(grow_out<hrow(l) - mu>(c), (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y));
     }
     return y;
 }
@@ -98,9 +142,17 @@ __device__ __forceinline__ void apply_reduced(const CtxR& c, int role) {
 }
 #endif
 
-__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbStepParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// bytes of one tile's shared-memory slice (stage buffers | forcing | scalars | mbarrier | table rings); 128-byte granular for kCW > 1
+__host__ __device__ constexpr size_t slice_bytes(int nbuf) {
+    const size_t b = (size_t)nbuf * kNRowR * kTNR * 16 + (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16 + kRingBytes;
+    return kCW > 1 ? (b + 127) / 128 * 128 : b;
+}
+
+__global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_cta[];
     const int nbuf = P.nstage == 1 ? 1 : kNBufRK;
+    const int sub = threadIdx.x / kThreads;                 // tile of this CTA (kCW > 1: one warp each)
+    unsigned char* smem_raw = smem_cta + (kCW > 1 ? (size_t)sub * slice_bytes(nbuf) : 0);
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* forc = bufs + (size_t)nbuf * kNRowR * kTNR;
     double* scal = reinterpret_cast<double*>(forc + kNF * kTNR);
@@ -108,9 +160,15 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
     double2* rings = reinterpret_cast<double2*>(mbar + 2);          // loop mode: [warps][2][pairs per item]
     (void)rings;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x % kThreads, warp = tid >> 5;
     const int t = tid & 31;                           // node within tile
-    const long long node0 = (long long)blockIdx.x * kTNR;
+    const long long node0 = ((long long)blockIdx.x * kCW + sub) * kTNR;
+#ifdef SFB_LS
+    constexpr bool kLS = kCW > 1;                     // lock step: the general-state decision is CTA wide, the reduced body has CTA barriers
+#else
+    constexpr bool kLS = false;
+#endif
+    if (kCW > 1 && node0 >= P.N) return;              // exited warps do not count at later CTA barriers
     const int nvalid = (int)min((long long)kTNR, P.N - node0);
     const bool valid = t < nvalid;
 
@@ -120,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    SFB_TILE_SYNC();
     if (warp == 0) {
         const uint32_t bytes = (uint32_t)nvalid * 16u;
         if (t == 0)
@@ -192,9 +250,9 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
         }
         bad = bad && valid;
     }
-    if (__syncthreads_or(bad)) {     // also orders the forcing preparation before the stages
+    if ((kCW > 1 && !kLS) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0)) {     // also orders the forcing preparation before the stages
         if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
-        __syncthreads();
+        SFB_TILE_SYNC();
         full_tile(P, node0, smem_raw);
         if (node0 + kTN < P.N) full_tile(P, node0 + kTN, smem_raw);
         return;
@@ -215,8 +273,10 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
     c.c0 = 0.0;
     c.ld_out = P.ld_out;
     c.ld_in = P.ld_in;
+    c.ldo32 = (unsigned)P.ld_out;
+    c.ldi32 = (unsigned)P.ld_in;
     c.gout = P.nlm_out + node0 + t;
-    c.gin = P.nlm_in + node0 + t;
+    c.gin = P.nlm_in + node0 + (SFB_N0ALL && !valid ? 0 : t);
     c.ap = bufs + (size_t)(nbuf - 1) * kNRowR * kTNR + t;
 
     for (int s = 0; s < P.nstage; ++s) {
@@ -252,13 +312,13 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
             }
         }
         if (kR > 1) {
-            __syncthreads();
+            SFB_TILE_SYNC();
             c.c0 = scal[SC_C0 * kTNR + t];
         }
 #endif
         apply_reduced(c, warp);
         // one role: every lane reads and writes only its own node's column -- no barrier between stages
-        if (kR > 1 && !c.last) __syncthreads();
+        if (kR > 1 && !c.last) SFB_TILE_SYNC();
     }
 }
 
@@ -266,13 +326,14 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
 
 extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
     static bool attr_done[64] = {false};
-    const size_t fixed = (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16 + kRingBytes;
-    const size_t per_buf = (size_t)kNRowR * kTNR * 16;
     const int nbuf_rk = kNBufRK;
-    const size_t smem_max = nbuf_rk * per_buf + fixed;
+    const size_t smem_max = slice_bytes(nbuf_rk) * kCW;
     // the general-path fallback (full_tile, 16 nodes, both row planes, both forcing blocks) uses the same bytes
     static_assert((size_t)kNRow * kTN == (size_t)kNRowR * kTNR && 2 * kNF * kTN == kNF * kTNR, "fallback must fit the reduced layout");
     if (smem_max > 227 * 1024) return cudaErrorInvalidConfiguration;
+#ifdef SFB_A32
+    if (Pin.ld_in >= (1LL << 32) || Pin.ld_out >= (1LL << 32)) return cudaErrorInvalidValue;   // 32-bit row strides
+#endif
     cudaError_t e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -288,7 +349,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
 #endif
     P.n0_global = 1;
     const int nbuf = P.nstage == 1 ? 1 : nbuf_rk;
-    const size_t smem = nbuf * per_buf + fixed;
+    const size_t smem = slice_bytes(nbuf) * kCW;
     {
         static SfbRegConst last[64];
         static bool have[64] = {false};
@@ -300,7 +361,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         }
     }
     if (P.N <= 0) return cudaSuccess;
-    const long long ntile = (P.N + kTNR - 1) / kTNR;
-    step_kernel_r<<<(unsigned)ntile, kThreads, smem, st>>>(P);
+    const long long ntile = (P.N + (long long)kTNR * kCW - 1) / ((long long)kTNR * kCW);
+    step_kernel_r<<<(unsigned)ntile, kThreads * kCW, smem, st>>>(P);
     return cudaGetLastError();
 }

@@ -63,6 +63,20 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if len(sys.argv) > 2:
         V = [int(x) for x in sys.argv[2].split(",")]
+    if which == "8x":       # headline kernels only (L=8, LROT+REG)
+        run(8, 1_000_000, ("lrot", "reg"), "rk4", V, steps=20)
+        run(8, 1_000_000, ("lrot", "reg"), "euler", V, steps=20)
+    if which == "4r":       # two-lane reduced kernels (L = 6, 8 with DDRX)
+        for L in (8, 6):
+            run(L, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=20)
+            run(L, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V, steps=10)
+    if which == "exp":      # the experimental variants of build.py EXP (SFB_EXP_VARIANTS=1)
+        for L, N in ((8, 1_000_000), (4, 2_000_000), (6, 1_000_000), (10, 1_000_000), (12, 500_000)):
+            run(L, N, ("lrot", "reg"), "rk4", V, steps=20)
+            run(L, N, ("lrot", "reg"), "euler", V, steps=20)
+        for L in (4, 6):
+            run(L, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=20)
+            run(L, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V, steps=20)
     if which == "small":
         for L in (4, 6, 10):
             run(L, 1_000_000, ("lrot", "reg"), "rk4", V)
