@@ -177,9 +177,17 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None):
-    """device-resident timing of one config; returns (ms_per_step_local, launches_per_step, n)"""
-    L, _, terms, scheme, eij, _ = CONFIGS[cfg]
+def rnlm_rows(L):
+    """rows of nlm that make up the reduced form (m >= 0; src/reducedform.f90:160-187)"""
+    lm = [(l, m) for l in range(0, L + 1, 2) for m in range(-l, l + 1)]
+    return [lm.index((l, m)) for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+
+
+def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None, reduced=False, scheme=None):
+    """device-resident timing of one config; returns (ms_per_step_local, launches_per_step, n).
+    reduced=True: the state is kept in reduced form (rnlm) and stepped with step_rnlm_arr_dev."""
+    L, _, terms, scheme0, eij, _ = CONFIGS[cfg]
+    scheme = scheme or scheme0
     lm, n = sf.init(L)
     u, t = synth_forcing(N, 20260817 + rank)
     ug = torch.from_numpy(np.ascontiguousarray(u.transpose(2, 1, 0))).cuda()     # (3,3,N): [k,i,p]
@@ -190,12 +198,17 @@ def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None):
     # 50 spin-up steps from isotropy so that every coefficient is non-zero
     for _ in range(50):
         sf.step_arr_dev(nlm, ug, tau, dt=DT, Gamma0=4.0, Lambda=1.0, terms=terms, scheme="euler")
+    stepf = sf.step_arr_dev
+    if reduced:
+        nlm = nlm[torch.tensor(rnlm_rows(L), device="cuda")].contiguous()
+        stepf = sf.step_rnlm_arr_dev
+        n = nlm.shape[0]
     eout = torch.empty((6, N), dtype=torch.float64, device="cuda") if eij else None
     eiv = torch.empty((3, 3, N), dtype=torch.float64, device="cuda") if eij else None
     lam = torch.empty((3, N), dtype=torch.float64, device="cuda") if eij else None
 
     def one():
-        sf.step_arr_dev(nlm, ug, tau, **kw)
+        stepf(nlm, ug, tau, **kw)
         if eij:
             sf.Eij_eigenframe_arr_dev(nlm, GRAIN, ALPHA, 1, out=eout, ei=eiv, lami=lam)
 
@@ -217,11 +230,15 @@ def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None):
     return ms, (2 if eij else 1), n, finite
 
 
-def time_e2e(sf, torch, cfg, N, rank, steps, warmup):
+def time_e2e(sf, torch, cfg, N, rank, steps, warmup, reduced=False):
     """the same step through the host-pointer C-ABI call: pinned host buffers, H2D of state + forcing and
-    D2H of the new state inside the timed region, every step"""
+    D2H of the new state inside the timed region, every step.  reduced=True: sfb_step_rnlm_arr on reduced-form states."""
     L, _, terms, scheme, eij, _ = CONFIGS[cfg]
     lm, n = sf.init(L)
+    hstep = sf.step_arr
+    if reduced:
+        n = sf.rnlm_len()
+        hstep = sf.step_rnlm_arr
     u, t = synth_forcing(N, 20260817 + rank)
 
     def pinned(shape, dtype):
@@ -237,15 +254,15 @@ def time_e2e(sf, torch, cfg, N, rank, steps, warmup):
         tp = pinned((3, 3, N), torch.float64).transpose(2, 1, 0)
         tp[:] = t
     kw = dict(dt=DT, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
-    x = sf.step_arr(x, ugp, tp, **dict(kw, scheme="euler", nsteps=20))
+    x = hstep(x, ugp, tp, **dict(kw, scheme="euler", nsteps=20))
     xin = pinned((n, N), torch.complex128).T
     xin[:] = x
     xout = pinned((n, N), torch.complex128).T
     for _ in range(warmup):
-        sf.step_arr(xin, ugp, tp, out=xout, **kw)
+        hstep(xin, ugp, tp, out=xout, **kw)
     t0 = time.perf_counter()
     for _ in range(steps):
-        out = sf.step_arr(xin, ugp, tp, out=xout, **kw)
+        out = hstep(xin, ugp, tp, out=xout, **kw)
         if eij:
             sf.Eij_eigenframe_arr(out, GRAIN, ALPHA, 1)
     el = time.perf_counter() - t0
@@ -359,6 +376,22 @@ def main():
                                       "finite": fin2}
             except Exception as ex:   # noqa
                 extra["cfg%d" % c] = {"error": str(ex)[:200]}
+        # the headline workload on reduced-form states (rows m >= 0 only; the FE couplers' state representation)
+        try:
+            r = (L + 2) ** 2 // 4
+            rr = {}
+            for sc in ("rk4", "euler"):
+                m3, _, _, fin3 = time_config(sf, torch, cfg, N, rank, 10, 3, reduced=True, scheme=sc)
+                rr[sc] = {"ms_per_step": m3, "node_updates_per_s": N / (m3 * 1e-3), "alg_bytes_per_node_step": 32 * r + 72,
+                          "hbm_gbs_alg": (32 * r + 72) * N / (m3 * 1e-3) / 1e9, "finite": fin3}
+            if not eij:
+                sec3, h3, d3 = time_e2e(sf, torch, cfg, N, rank, 3, 1, reduced=True)
+                rr["e2e"] = {"value": N / sec3, "unit": "node-updates/s", "h2d_bytes_per_step": h3, "d2h_bytes_per_step": d3,
+                             "api": "sfb_step_rnlm_arr (host pointers)"}
+            rr["workload"] = "%s, state in reduced form (rnlm: %d of %d coefficient rows), sfb_step_rnlm_arr(_dev)" % (desc, r, n)
+            extra["rnlm"] = rr
+        except Exception as ex:   # noqa
+            extra["rnlm"] = {"error": str(ex)[:200]}
         # stand-alone Eij evals/s (a2 -> eigenframe -> 6 Sachs/Taylor factors per node)
         try:
             lm, n8 = sf.init(8)

@@ -32,6 +32,12 @@ module specfab_b200
             integer(c_int64_t), value :: N, ld
             type(sfb_step_opts), intent(in) :: opts
         end function
+        ! the same step on reduced-form states rnlm(N, rnlm_len) (src/reducedform.f90:160-187)
+        integer(c_int) function sfb_step_rnlm_arr(rnlm_in, rnlm_out, N, ld, ugrad, tau, opts) bind(c, name='sfb_step_rnlm_arr')
+            import; type(c_ptr), value :: rnlm_in, rnlm_out, ugrad, tau
+            integer(c_int64_t), value :: N, ld
+            type(sfb_step_opts), intent(in) :: opts
+        end function
         integer(c_int) function sfb_a2_arr(nlm, N, ld, a2) bind(c, name='sfb_a2_arr')      ! src/specfabpy.f90:583
             import; type(c_ptr), value :: nlm, a2; integer(c_int64_t), value :: N, ld
         end function
@@ -105,6 +111,18 @@ contains
         o = sfb_step_opts(dt, iota, zeta, 1.0d0, Gamma0, Lambda, c_null_ptr, c_null_ptr, terms, scheme, 1, 0)
         call check(sfb_step_arr(c_loc(nlm), c_loc(nlm), int(size(nlm,1),c_int64_t), int(size(nlm,1),c_int64_t), &
                                 c_loc(ugrad), c_loc(tau), o), 'step_arr')
+    end subroutine
+
+    ! the same for states kept in reduced form (what src/specfabpy/fenics/CPO.py holds): rnlm(N, rnlm_len), m >= 0 only
+    subroutine step_rnlm_arr(rnlm, ugrad, tau, dt, iota, zeta, Gamma0, Lambda, terms, scheme)
+        complex(kind=dp), intent(inout), target :: rnlm(:,:)         ! (N, rnlm_len)
+        real(kind=dp), intent(in), target       :: ugrad(:,:,:), tau(:,:,:)   ! (N,3,3)
+        real(kind=dp), intent(in)               :: dt, iota, zeta, Gamma0, Lambda
+        integer, intent(in)                     :: terms, scheme
+        type(sfb_step_opts) :: o
+        o = sfb_step_opts(dt, iota, zeta, 1.0d0, Gamma0, Lambda, c_null_ptr, c_null_ptr, terms, scheme, 1, 0)
+        call check(sfb_step_rnlm_arr(c_loc(rnlm), c_loc(rnlm), int(size(rnlm,1),c_int64_t), int(size(rnlm,1),c_int64_t), &
+                                     c_loc(ugrad), c_loc(tau), o), 'step_rnlm_arr')
     end subroutine
 
     ! drop-in for Eij_tranisotropic_arr (src/specfabpy.f90:474-486)

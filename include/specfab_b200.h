@@ -80,6 +80,17 @@ int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t l
                      const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
                      const sfb_step_opts* opts, void* stream);
 
+/* The same fused step on REDUCED-FORM states: rnlm(N, rnlm_len) holds the m >= 0 coefficients of a real-valued ODF, row
+ * (l, m) at (l/2)^2 + m -- the layout of nlm_to_rnlm / rnlm_to_nlm (src/reducedform.f90:160-187, src/specfabpy.f90:1076-1094),
+ * the representation the FE couplers keep their state in (src/specfabpy/fenics/CPO.py:103-118, 339-365).  Equal to
+ * nlm_to_rnlm(step(rnlm_to_nlm(rnlm))) bit for bit, but only (L+2)^2/4 instead of (L+1)(L+2)/2 coefficient rows are read,
+ * written and (host variant) cross PCIe; Im n_l^0 is taken as 0.  ld = leading (node) dimension of the rnlm arrays. */
+int sfb_step_rnlm_arr(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld,
+                      const double* ugrad, const double* tau, const sfb_step_opts* opts);
+int sfb_step_rnlm_arr_dev(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                          const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
+                          const sfb_step_opts* opts, void* stream);
+
 /* One call per FE time step (SURVEY.md 8b "step_moments_Eij_arr", BASELINE config 5): the fused step above, then on the
  * new state a2 (optional), a4 (optional), the a2 eigenframe (ei, lami: optional, both or none) and the eigenenhancements
  * Eij (N,6) in that frame -- what src/specfabpy/fenics/CPO.py:evolve + src/specfabpy/fenics/enhancementfactor.py:101-128 do

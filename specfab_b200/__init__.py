@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "dndt_LATROT", "dndt_DDRX", "dndt_CDRX", "dndt_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
-           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "build_info", "layout_nlm", "layout_mat",
+           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "step_moments_Eij_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
@@ -96,8 +96,23 @@ def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.
     (written into `out` when given: a Fortran-ordered (N,nlm_len) complex128 array, e.g. pinned memory).
     Batches  nlm + dt*matmul(M_LROT + Gamma0*M_DDRX + Lambda*M_CDRX + M_REG, nlm)
     (reference per node: src/specfabpy/integrator.py:73-77, src/dynamics.f90:99-110)."""
+    return _step_host(False, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out)
+
+
+def step_rnlm_arr(rnlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.0, Lambda=0.0,
+                  terms=("lrot", "reg"), scheme="euler", nsteps=1, out=None):
+    """step_arr on REDUCED-FORM states: rnlm (N, rnlm_len) complex128 holds the m >= 0 coefficients of a real-valued ODF
+    (nlm_to_rnlm / rnlm_to_nlm, src/reducedform.f90:160-187 -- the state representation of the FE couplers,
+    src/specfabpy/fenics/CPO.py).  Same arguments and result as step_arr with every state array in reduced form;
+    equals nlm_to_rnlm_arr(step_arr(rnlm_to_nlm_arr(rnlm), ...)) bit for bit and moves 25/45 (L=8) of the state bytes."""
+    return _step_host(True, rnlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out)
+
+
+def _step_host(reduced, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out):
     n = _need_init()
     lib = _lib.load()
+    if reduced:
+        n = rnlm_len()
     nlm_f = _farr(nlm, np.complex128, (n,))
     N = nlm_f.shape[0]
     ug = _farr(ugrad, np.float64, (3, 3))
@@ -122,8 +137,8 @@ def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.
     if out is None:
         out = np.empty((N, n), dtype=np.complex128, order="F")
     elif out.shape != (N, n) or out.dtype != np.complex128 or not out.flags.f_contiguous:
-        raise ValueError("out must be a Fortran-ordered complex128 array of shape (N, nlm_len)")
-    _lib.check(lib.sfb_step_arr(nlm_f.ctypes.data, out.ctypes.data, N, N, ug.ctypes.data,
+        raise ValueError("out must be a Fortran-ordered complex128 array of shape (N, %s)" % ("rnlm_len" if reduced else "nlm_len"))
+    _lib.check((lib.sfb_step_rnlm_arr if reduced else lib.sfb_step_arr)(nlm_f.ctypes.data, out.ctypes.data, N, N, ug.ctypes.data,
                                 ta.ctypes.data if ta is not None else None, C.byref(o)))
     return out
 
@@ -573,11 +588,23 @@ def step_arr_dev(nlm, ugrad, tau=None, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=
     """Device-resident fused step.  nlm: (nlm_len, N) complex128 CUDA tensor (library layout),
     ugrad/tau: (3,3,N) float64 CUDA tensors (layout_mat).  out defaults to in-place.
     Gamma0/Lambda: scalars or (N,) float64 CUDA tensors.  Asynchronous on the current stream."""
+    return _step_dev(False, nlm, ugrad, tau, out, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps)
+
+
+def step_rnlm_arr_dev(rnlm, ugrad, tau=None, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.0, Lambda=0.0,
+                      terms=("lrot", "reg"), scheme="euler", nsteps=1):
+    """step_arr_dev on reduced-form states: rnlm (rnlm_len, N) complex128 CUDA tensor (rows m >= 0, see step_rnlm_arr)."""
+    return _step_dev(True, rnlm, ugrad, tau, out, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps)
+
+
+def _step_dev(reduced, nlm, ugrad, tau, out, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps):
     import torch
     n = _need_init()
     lib = _lib.load()
+    if reduced:
+        n = rnlm_len()
     if nlm.dtype != torch.complex128 or not nlm.is_cuda or not nlm.is_contiguous() or nlm.shape[0] != n:
-        raise ValueError("nlm must be a contiguous CUDA complex128 tensor of shape (nlm_len, N)")
+        raise ValueError("state must be a contiguous CUDA complex128 tensor of shape (%s, N)" % ("rnlm_len" if reduced else "nlm_len"))
     N = nlm.shape[1]
     if out is None:
         out = nlm
@@ -594,7 +621,7 @@ def step_arr_dev(nlm, ugrad, tau=None, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=
 
     g0p, lamp = vec(Gamma0), vec(Lambda)
     o = _opts(dt, iota, zeta, nu, 0.0 if g0p else Gamma0, 0.0 if lamp else Lambda, terms, scheme, nsteps, g0p, lamp)
-    _lib.check(lib.sfb_step_arr_dev(nlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
+    _lib.check((lib.sfb_step_rnlm_arr_dev if reduced else lib.sfb_step_arr_dev)(nlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
                                     tau.data_ptr() if tau is not None else None, N, C.byref(o), _stream_ptr()))
     return out
 

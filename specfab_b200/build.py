@@ -64,10 +64,10 @@ EXTRA = {
 }
 # variants under test (SFB_EXP_VARIANTS=1)
 EXP = {
-    (12, 1): [(131, -4, 32, 4, "imm+ch4+r3", False), (132, -4, 32, 3, "imm+ch4+r3", False), (133, -4, 32, 3, "imm+ch4+r4", False),
-              (135, -4, 32, 4, "imm+ch4+r2", False)],
-    (20, 1): [(131, -4, 32, 2, "imm+ch4+r6", False), (132, -4, 32, 2, "imm+ch4+r4", False),
-              (134, -4, 32, 2, "imm+ch4+r8", False)],
+    # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
+    # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
+    # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
+    # tiles or per-block lock step (0.73-0.75 ms, same as the default)
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;

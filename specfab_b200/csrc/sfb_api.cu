@@ -184,9 +184,10 @@ static int check_opts(const sfb_step_opts* o) {
     return SFB_OK;
 }
 
-int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
-                     const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
-                     const sfb_step_opts* o, void* stream) {
+// rio = 1: the state arrays are in reduced form (rows m >= 0 only, sfb_step_rnlm_arr*)
+static int step_dev_impl(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                         const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
+                         const sfb_step_opts* o, void* stream, int rio) {
     if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
     int rc = check_opts(o);
     if (rc) return rc;
@@ -199,6 +200,8 @@ int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t l
     const SfbStepEntry* ent = find_step(g.L, ddrx, o->scheme == SFB_RK4 ? 4 : 1);
     if (!ent) return fail(SFB_ENOTBUILT, "step kernel for this L not compiled");
     SfbStepParams P;
+    P.rio = rio;
+    P.ktab = nullptr; P.raw_ok = 0; P.n0_global = 0;
     P.nlm_in = reinterpret_cast<const double2*>(nlm_in);
     P.nlm_out = reinterpret_cast<double2*>(nlm_out);
     P.ugrad = ugrad;
@@ -214,11 +217,24 @@ int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t l
     P.use_reg = (o->terms & SFB_REG) ? 1 : 0;
     for (int s = 0; s < o->nsteps; ++s) {
         cudaError_t e = ent->fn(P, g.reg, (cudaStream_t)stream);
+        if (e == cudaErrorNotSupported) return fail(SFB_EINVAL, "the selected kernel variant (sfb_set_variant) has no reduced-form I/O");
         if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
         P.nlm_in = P.nlm_out;   // subsequent sub-steps run in place
         P.ld_in = P.ld_out;
     }
     return SFB_OK;
+}
+
+int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                     const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
+                     const sfb_step_opts* o, void* stream) {
+    return step_dev_impl(nlm_in, nlm_out, N, ld_in, ld_out, ugrad, ld_u, tau, ld_t, o, stream, 0);
+}
+
+int sfb_step_rnlm_arr_dev(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                          const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
+                          const sfb_step_opts* o, void* stream) {
+    return step_dev_impl(rnlm_in, rnlm_out, N, ld_in, ld_out, ugrad, ld_u, tau, ld_t, o, stream, 1);
 }
 
 static int ensure_slot(Slot& s, size_t bytes_n, size_t nodes) {
@@ -243,8 +259,8 @@ static int ensure_slot(Slot& s, size_t bytes_n, size_t nodes) {
 }
 
 // Host-pointer variant: chunks of nodes are pipelined over 3 streams (H2D | kernel | D2H overlap).
-int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
-                 const double* ugrad, const double* tau, const sfb_step_opts* o) {
+static int step_host_impl(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
+                          const double* ugrad, const double* tau, const sfb_step_opts* o, int rio) {
     if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
     int rc = check_opts(o);
     if (rc) return rc;
@@ -255,7 +271,7 @@ int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (g_stage.dev != dev) { g_stage.release(); g_stage.dev = dev; }
-    const int n = g.n;
+    const int n = rio ? (g.L / 2 + 1) * (g.L / 2 + 1) : g.n;      // coefficient rows that cross PCIe
     static int64_t chunk_nodes = 0;      // nodes per pipeline stage (H2D | kernel | D2H on rotating streams); SFB_CHUNK overrides
     if (!chunk_nodes) { const char* ev = getenv("SFB_CHUNK"); chunk_nodes = ev ? atoll(ev) : (1 << 16); if (chunk_nodes < 1024) chunk_nodes = 1024; }
     const int64_t chunk = std::min<int64_t>(N, chunk_nodes);
@@ -272,13 +288,23 @@ int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
         sfb_step_opts oo = *o;
         if (o->gamma0_arr) { CK(cudaMemcpyAsync(s.g0, o->gamma0_arr + p0, c * 8, cudaMemcpyHostToDevice, s.st)); oo.gamma0_arr = s.g0; }
         if (o->lambda_arr) { CK(cudaMemcpyAsync(s.lam, o->lambda_arr + p0, c * 8, cudaMemcpyHostToDevice, s.st)); oo.lambda_arr = s.lam; }
-        rc = sfb_step_arr_dev(s.nin, s.nout, c, chunk, chunk, s.ug, chunk, (ddrx && tau) ? s.tau : nullptr, chunk, &oo, s.st);
+        rc = step_dev_impl(s.nin, s.nout, c, chunk, chunk, s.ug, chunk, (ddrx && tau) ? s.tau : nullptr, chunk, &oo, s.st, rio);
         if (rc) return rc;
         CK(cudaMemcpy2DAsync(nlm_out + 2 * p0, ld * 16, s.nout, chunk * 16, c * 16, n, cudaMemcpyDeviceToHost, s.st));
     }
     for (auto& s : g_stage.s)
         if (s.st) CK(cudaStreamSynchronize(s.st));
     return SFB_OK;
+}
+
+int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
+                 const double* ugrad, const double* tau, const sfb_step_opts* o) {
+    return step_host_impl(nlm_in, nlm_out, N, ld, ugrad, tau, o, 0);
+}
+
+int sfb_step_rnlm_arr(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld,
+                      const double* ugrad, const double* tau, const sfb_step_opts* o) {
+    return step_host_impl(rnlm_in, rnlm_out, N, ld, ugrad, tau, o, 1);
 }
 
 int sfb_set_variant(int v) { g_variant = v; return SFB_OK; }

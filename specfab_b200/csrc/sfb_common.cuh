@@ -25,6 +25,8 @@ struct SfbStepParams {
     const double2* ktab;     // set by the launcher in gtab mode
     int raw_ok;              // set by the launcher: forcing planes can be staged with 1-D TMA bulk copies
     int n0_global;           // set by the launcher: RK4 re-reads n0 from global (3 smem buffers)
+    int rio;                 // reduced I/O (sfb_step_rnlm_arr): nlm_in / nlm_out hold the rows m >= 0 only, row (l, m) at
+                             // (l/2)^2 + m (src/reducedform.f90:160-187); reduced kernels only
 };
 
 // per-L regularisation constants, set by sfb_init (host pow(), like the reference's libm)

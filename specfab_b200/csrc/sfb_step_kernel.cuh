@@ -308,6 +308,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
+    if (Pin.rio) return cudaErrorNotSupported;      // reduced-form arrays: reduced kernels only
     SfbStepParams P = Pin;
 #ifdef SFB_LOOP
     { void* tp = nullptr; e = cudaGetSymbolAddress(&tp, sfb_ltab); if (e != cudaSuccess) return e; P.ktab = reinterpret_cast<const double2*>(tp); }

@@ -263,6 +263,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
+    if (Pin.rio) return cudaErrorNotSupported;      // reduced-form arrays: reduced kernels only
     SfbStepParams P = Pin;
 #ifdef SFB_GTAB
     { void* tp = nullptr; e = cudaGetSymbolAddress(&tp, sfb_gtab); if (e != cudaSuccess) return e; P.ktab = reinterpret_cast<const double2*>(tp); }

@@ -59,10 +59,14 @@ __device__ __forceinline__ double gload(const double* p) { return *p; }
 __device__ __forceinline__ void gstore(double* p, double v) { *p = v; }
 #endif
 
-template <int l, int mu>
+// RIO ("reduced I/O", sfb_step_rnlm_arr): the global arrays hold the rows m >= 0 only, row (l, m) at (l/2)^2 + m
+template <int l, int mu, bool RIO>
+__host__ __device__ constexpr int grow_idx() { return RIO ? pslot(l, mu) : hrow(l) + mu; }
+
+template <int l, int mu, bool RIO>
 __device__ __forceinline__ double n0_load_r(const CtxR& c) {
     double v = 0.0;
-    if (c.ld_n0) v = gload(grow_in<hrow(l) + mu>(c));
+    if (c.ld_n0) v = gload(grow_in<grow_idx<l, mu, RIO>()>(c));
     return v;
 }
 template <int l, int mu>
@@ -75,7 +79,7 @@ __device__ __forceinline__ double acc_load_r(const CtxR& c) {
     return v;
 #endif
 }
-template <int l, int mu>
+template <int l, int mu, bool RIO>
 __device__ __forceinline__ void row_out_r(const CtxR& c, double mine, double theirs, double z, double n0, double acc) {
     const double recv = __shfl_xor_sync(0xffffffffu, theirs, 1);
     double k = fma(c.sigma, recv, mine);
@@ -96,25 +100,27 @@ __device__ __forceinline__ void row_out_r(const CtxR& c, double mine, double the
     const double res = A;
 #endif
     if (c.last && c.valid) {
-        gstore(grow_out<hrow(l) + mu>(c), res);
+        gstore(grow_out<grow_idx<l, mu, RIO>()>(c), res);
         // mirror row (-1)^mu conj: the re lane keeps the parity sign, the im lane gets the opposite one
-        if (mu != 0) gstore(grow_out<hrow(l) - mu>(c), ((mu & 1) != 0) == c.isim ? res : -res);
+        if (mu != 0 && !RIO) gstore(grow_out<hrow(l) - mu>(c), ((mu & 1) != 0) == c.isim ? res : -res);
     }
 }
-#define SFB_RROW_OUT4(l, mu, m, t, z, q, r) row_out_r<l, mu>(c, m, t, z, q, r)
-#define SFB_RN0_LOAD(l, mu) n0_load_r<l, mu>(c)
+// (RIO: template parameter of the enclosing apply_reduced)
+#define SFB_RROW_OUT4(l, mu, m, t, z, q, r) row_out_r<l, mu, RIO>(c, m, t, z, q, r)
+#define SFB_RN0_LOAD(l, mu) n0_load_r<l, mu, RIO>(c)
 #define SFB_RACC_LOAD(l, mu) acc_load_r<l, mu>(c)
 // forcing of a mirrored column block: sign = (-1)^nu, times +1 / -1 on the re / im lane
 #define SFB_FMIR(fidx, sign) make_double2(fz[(fidx) * SFB_TNR].x * ((sign) * c.em), fz[(fidx) * SFB_TNR].y * ((sign) * c.em))
 
+template <bool RIO>
 __device__ __forceinline__ void apply_reduced(const CtxR& c) {
     const double* __restrict__ yp = c.yp;
     const double2* __restrict__ fz = c.fz;
 #include SFB_APPLY_INC_R
 }
 
-__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbStepParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+template <bool RIO>
+__device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned char* smem_raw) {
     const int nbuf = P.nstage == 1 ? 1 : (SFB_HORNER ? 2 : 3);
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* forc = bufs + (size_t)nbuf * kNRowR * kTNR;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
             while ((h + 1) * (h + 1) <= r) ++h;
             const int l = 2 * h, m = r - h * h;
             const uint32_t dst = smem_u32(bufs + (size_t)r * kTNR);
-            const double2* src = P.nlm_in + (long long)(hrow(l) + m) * P.ld_in + node0;
+            const double2* src = P.nlm_in + (long long)(RIO ? r : hrow(l) + m) * P.ld_in + node0;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
 
     // ---- real-ODF symmetry of the input to round-off, each lane tests its own component of the mirror rows
     bool bad = false;
-    if (valid) {
+    if (!RIO && valid) {
         const double* gneg = reinterpret_cast<const double*>(P.nlm_in + node0 + nl) + comp;
         const double tol = kSymTol * fabs(reinterpret_cast<const double*>(bufs)[2 * nl]);
 #pragma unroll
@@ -190,7 +196,9 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
                 }
         }
     }
-    if (__syncthreads_or(bad)) {
+    if (RIO) {                          // a reduced-form state is symmetric by construction: only order the forcing preparation
+        __syncthreads();
+    } else if (__syncthreads_or(bad)) {
         if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
         __syncthreads();
         full_tile(P, node0, smem_raw);
@@ -249,9 +257,19 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbSte
         __syncthreads();
         c.c0 = scal[SC_C0 * kTNR + nl];
 #endif
-        apply_reduced(c);
+        apply_reduced<RIO>(c);
         if (!c.last) __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_r(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    step_tile_r<false>(P, smem_raw);
+}
+// the same step on reduced-form arrays (rows m >= 0 in, rows m >= 0 out)
+__global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_rr(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    step_tile_r<true>(P, smem_raw);
 }
 
 }  // namespace
@@ -274,6 +292,8 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     if (!attr_done[dev]) {
         e = cudaFuncSetAttribute(step_kernel_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(step_kernel_rr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
     SfbStepParams P = Pin;
@@ -292,6 +312,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     }
     if (P.N <= 0) return cudaSuccess;
     const long long ntile = (P.N + kTNR - 1) / kTNR;
-    step_kernel_r<<<(unsigned)ntile, kThreads, smem, st>>>(P);
+    if (P.rio) step_kernel_rr<<<(unsigned)ntile, kThreads, smem, st>>>(P);
+    else step_kernel_r<<<(unsigned)ntile, kThreads, smem, st>>>(P);
     return cudaGetLastError();
 }

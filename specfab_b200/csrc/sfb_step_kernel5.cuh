@@ -364,6 +364,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         grid_max[dev] = nsm > 0 ? nsm : 148;
         attr_done[dev] = true;
     }
+    if (Pin.rio) return cudaErrorNotSupported;      // reduced-form arrays: reduced kernels only
     SfbStepParams P = Pin;
     P.n0_global = 1;
     P.raw_ok = (((uintptr_t)P.ugrad & 15) == 0 && (P.ld_u % 2) == 0 &&

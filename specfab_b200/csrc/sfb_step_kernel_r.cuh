@@ -76,13 +76,18 @@ __device__ __forceinline__ double2 gload(const double2* p) { return *p; }
 __device__ __forceinline__ void gstore(double2* p, double2 v) { *p = v; }
 #endif
 
-template <int l, int mu>
+// RIO ("reduced I/O", sfb_step_rnlm_arr): the global arrays hold the rows m >= 0 only, row (l, m) at (l/2)^2 + m -- the
+// rnlm layout of src/reducedform.f90:160-187 -- so nothing is tested, no mirror row is read or written
+template <int l, int mu, bool RIO>
+__host__ __device__ constexpr int grow_idx() { return RIO ? pslot(l, mu) : hrow(l) + mu; }
+
+template <int l, int mu, bool RIO>
 __device__ __forceinline__ double2 n0_load_r(const CtxR& c) {
 #if SFB_N0ALL
-    return gload(grow_in<hrow(l) + mu>(c));      // every stage, every lane (c.gin of a lane beyond N points at the tile's first node)
+    return gload(grow_in<grow_idx<l, mu, RIO>()>(c));      // every stage, every lane (c.gin of a lane beyond N points at the tile's first node)
 #else
     double2 v = make_double2(0.0, 0.0);
-    if (c.ld_n0) v = gload(grow_in<hrow(l) + mu>(c));
+    if (c.ld_n0) v = gload(grow_in<grow_idx<l, mu, RIO>()>(c));
     return v;
 #endif
 }
@@ -96,7 +101,7 @@ __device__ __forceinline__ double2 acc_load_r(const CtxR& c) {
 }
 // finalize one row; returns the stage output y.  STORE: write y to the next-stage buffer now (two-buffer scheme);
 // otherwise the caller parks it in a register and commits it later (in-place scheme, SFB_INPLACE)
-template <int l, int mu, bool STORE>
+template <int l, int mu, bool STORE, bool RIO>
 __device__ __forceinline__ double2 row_out_r(const CtxR& c, double kr, double ki, double zr, double zi, double2 n0, double2 acc) {
     double d = fma(c.lam, -(double)(l * (l + 1)), c.c0);
     d = fma(c.rm, c_reg.regdiag[l / 2], d);
@@ -120,21 +125,24 @@ __device__ __forceinline__ double2 row_out_r(const CtxR& c, double kr, double ki
     const double2 res = A;
 #endif
     if (c.last && c.valid) {
-        gstore(grow_out<hrow(l) + mu>(c), res);
-        if (mu != 0)      // mirror row: (-1)^mu conj
+        gstore(grow_out<grow_idx<l, mu, RIO>()>(c), res);
+        if (mu != 0 && !RIO)      // mirror row: (-1)^mu conj
             gstore(grow_out<hrow(l) - mu>(c), (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y));
     }
     return y;
 }
-#define SFB_RROW_PRE(l, mu, q, r) const double2 q = n0_load_r<l, mu>(c), r = acc_load_r<l, mu>(c)
-#define SFB_RROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out_r<l, mu, true>(c, ar, ai, zr, zi, q, r)
-#define SFB_RROW_OUTQ(l, mu, ar, ai, zr, zi, q, r, o) o = row_out_r<l, mu, false>(c, ar, ai, zr, zi, q, r)
+// (RIO: template parameter of the enclosing apply_reduced)
+#define SFB_RROW_PRE(l, mu, q, r) const double2 q = n0_load_r<l, mu, RIO>(c), r = acc_load_r<l, mu>(c)
+#define SFB_RROW_OUT(l, mu, ar, ai, zr, zi, q, r) row_out_r<l, mu, true, RIO>(c, ar, ai, zr, zi, q, r)
+#define SFB_RROW_OUTQ(l, mu, ar, ai, zr, zi, q, r, o) o = row_out_r<l, mu, false, RIO>(c, ar, ai, zr, zi, q, r)
 #define SFB_RROW_COMMIT(l, mu, o) do { if (!c.last) c.op[pslot(l, mu) * kTNR] = o; } while (0)
 
 #ifdef SFB_LOOP
 #include "sfb_step_loop_r.cuh"
-__device__ __forceinline__ void apply_reduced(const CtxR& c, int role) { loopk::apply_loop_r(c, role, kR, c.ring, (int)(threadIdx.x & 31)); }
+template <bool RIO>
+__device__ __forceinline__ void apply_reduced(const CtxR& c, int role) { loopk::apply_loop_r<RIO>(c, role, kR, c.ring, (int)(threadIdx.x & 31)); }
 #else
+template <bool RIO>
 __device__ __forceinline__ void apply_reduced(const CtxR& c, int role) {
     const double2* __restrict__ yp = c.yp;
     const double2* __restrict__ fz = c.fz;
@@ -148,8 +156,8 @@ __host__ __device__ constexpr size_t slice_bytes(int nbuf) {
     return kCW > 1 ? (b + 127) / 128 * 128 : b;
 }
 
-__global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const SfbStepParams P) {
-    extern __shared__ __align__(128) unsigned char smem_cta[];
+template <bool RIO>
+__device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned char* smem_cta) {
     const int nbuf = P.nstage == 1 ? 1 : kNBufRK;
     const int sub = threadIdx.x / kThreads;                 // tile of this CTA (kCW > 1: one warp each)
     unsigned char* smem_raw = smem_cta + (kCW > 1 ? (size_t)sub * slice_bytes(nbuf) : 0);
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const 
             while ((h + 1) * (h + 1) <= r) ++h;
             const int l = 2 * h, m = r - h * h;
             const uint32_t dst = smem_u32(bufs + (size_t)r * kTNR);
-            const double2* src = P.nlm_in + (long long)(hrow(l) + m) * P.ld_in + node0;
+            const double2* src = P.nlm_in + (long long)(RIO ? r : hrow(l) + m) * P.ld_in + node0;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
         }
@@ -198,11 +206,11 @@ __global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const 
     // ---- the mirror rows (m < 0) of this lane's node, for the symmetry test (warp 0): issued now, all loads in flight
     // together, consumed after the tile has landed (their latency hides behind the bulk copies and the forcing preparation)
     constexpr int kNNeg = kNCoef - kNRowR;
-    constexpr bool kBatchAll = kNNeg <= 42 && !SFB_DDRX;   // LROT kernels up to L = 12: every mirror row in registers
+    constexpr bool kBatchAll = kNNeg <= 42 && !SFB_DDRX && !RIO;   // LROT kernels up to L = 12: every mirror row in registers
                                                          // (the DDRX preparation needs the registers: per-degree batches there)
     double2 vneg[kBatchAll ? (kNNeg > 0 ? kNNeg : 1) : 1];
     const double2* gneg = P.nlm_in + node0 + (valid ? t : 0);
-    if (kBatchAll && warp == 0) {
+    if (!RIO && kBatchAll && warp == 0) {
 #pragma unroll
         for (int l = 2; l <= kL; l += 2)
 #pragma unroll
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const 
     // ---- real-ODF symmetry of the input to round-off (NaNs fail the test and take the general path)
     // (with several roles the degrees l are dealt to the warps; a single warp owns all of them and may have batched the loads)
     bool bad = false;
-    {
+    if (!RIO) {
         const double tol = kSymTol * fabs(bufs[t].x);
 #pragma unroll
         for (int l = 0; l <= kL; l += 2) {
@@ -250,7 +258,9 @@ __global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const 
         }
         bad = bad && valid;
     }
-    if ((kCW > 1 && !kLS) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0)) {     // also orders the forcing preparation before the stages
+    if (RIO) {                          // a reduced-form state is symmetric by construction: only order the forcing preparation
+        if (kR > 1) SFB_TILE_SYNC(); else __syncwarp();
+    } else if ((kCW > 1 && !kLS) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0)) {     // also orders the forcing preparation before the stages
         if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
         SFB_TILE_SYNC();
         full_tile(P, node0, smem_raw);
@@ -316,10 +326,20 @@ __global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const 
             c.c0 = scal[SC_C0 * kTNR + t];
         }
 #endif
-        apply_reduced(c, warp);
+        apply_reduced<RIO>(c, warp);
         // one role: every lane reads and writes only its own node's column -- no barrier between stages
         if (kR > 1 && !c.last) SFB_TILE_SYNC();
     }
+}
+
+__global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_r(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_cta[];
+    step_tile_r<false>(P, smem_cta);
+}
+// the same step on reduced-form arrays (rows m >= 0 in, rows m >= 0 out)
+__global__ void __launch_bounds__(kThreads * kCW, SFB_MINB) step_kernel_rr(const SfbStepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_cta[];
+    step_tile_r<true>(P, smem_cta);
 }
 
 }  // namespace
@@ -340,6 +360,8 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     dev &= 63;
     if (!attr_done[dev]) {
         e = cudaFuncSetAttribute(step_kernel_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(step_kernel_rr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
@@ -362,6 +384,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     }
     if (P.N <= 0) return cudaSuccess;
     const long long ntile = (P.N + (long long)kTNR * kCW - 1) / ((long long)kTNR * kCW);
-    step_kernel_r<<<(unsigned)ntile, kThreads * kCW, smem, st>>>(P);
+    if (P.rio) step_kernel_rr<<<(unsigned)ntile, kThreads * kCW, smem, st>>>(P);
+    else step_kernel_r<<<(unsigned)ntile, kThreads * kCW, smem, st>>>(P);
     return cudaGetLastError();
 }

@@ -10,6 +10,7 @@
 
 namespace loopk {
 
+template <bool RIO>
 __device__ __forceinline__ void row_out_rt_r(const CtxR& c, int l, int mu, bool rowok, double kr, double ki, double zr, double zi,
                                              double2 n0, double2 acc) {
     double d = fma(c.lam, -(double)(l * (l + 1)), c.c0);
@@ -30,9 +31,13 @@ __device__ __forceinline__ void row_out_rt_r(const CtxR& c, int l, int mu, bool 
     const double2 res = A;
 #endif
     if (rowok && c.last && c.valid) {
-        const long long h = (long long)(l * (l + 1) / 2);
-        c.gout[(h + mu) * c.ld_out] = res;
-        if (mu != 0) c.gout[(h - mu) * c.ld_out] = (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y);
+        if (RIO) {          // reduced-form output array: row (l, mu) at (l/2)^2 + mu, no mirror rows
+            c.gout[(long long)((l >> 1) * (l >> 1) + mu) * c.ld_out] = res;
+        } else {
+            const long long h = (long long)(l * (l + 1) / 2);
+            c.gout[(h + mu) * c.ld_out] = res;
+            if (mu != 0) c.gout[(h - mu) * c.ld_out] = (mu & 1) ? make_double2(-res.x, res.y) : make_double2(res.x, -res.y);
+        }
     }
 }
 
@@ -102,6 +107,7 @@ __device__ __forceinline__ void delta_sweep_r(const CtxR& c, const double2 (&fl)
 }
 
 // ring: this warp's private [2][kPairs] double2 area
+template <bool RIO>
 __device__ __forceinline__ void apply_loop_r(const CtxR& c, int role, int nroles, double2* ring, int lane) {
     int slot = 0;
     if (role < SFB_LT_NITEMS) ring_fetch(ring, c.ktab + (size_t)role * kPairs, lane);
@@ -135,7 +141,7 @@ __device__ __forceinline__ void apply_loop_r(const CtxR& c, int role, int nroles
             const bool rowok = l >= mu && l >= 0;
             n0[q] = make_double2(0.0, 0.0);
             acc[q] = make_double2(0.0, 0.0);
-            if (rowok && c.ld_n0) n0[q] = c.gin[(long long)(l * (l + 1) / 2 + mu) * c.ld_in];
+            if (rowok && c.ld_n0) n0[q] = c.gin[(long long)(RIO ? (l >> 1) * (l >> 1) + mu : l * (l + 1) / 2 + mu) * c.ld_in];
 #if !SFB_HORNER
             if (rowok && c.ld_acc) acc[q] = c.ap[((l >> 1) * (l >> 1) + mu) * kTNR];
 #endif
@@ -145,7 +151,7 @@ __device__ __forceinline__ void apply_loop_r(const CtxR& c, int role, int nroles
         for (int q = 0; q < kCH; ++q) {
             const int l = kL - 2 * (k * kCH + q);
             const bool rowok = l >= mu && l >= 0;
-            row_out_rt_r(c, rowok ? l : 0, mu, rowok, ar[q], ai[q], zr[q], zi[q], n0[q], acc[q]);
+            row_out_rt_r<RIO>(c, rowok ? l : 0, mu, rowok, ar[q], ai[q], zr[q], zi[q], n0[q], acc[q]);
         }
         __syncwarp();          // every lane is done with this slot before it is refilled two items later
         slot ^= 1;

@@ -57,3 +57,15 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")) and "gen" not in dirpath:
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import specfab_oracle" not in src and "oracle_c" not in src and "liboracle" not in src, f
+
+
+def test_fortran_shim_binds_only_declared_symbols():
+    """every bind(c, name='...') of the iso_c_binding shim must be a symbol the header declares"""
+    src = open(os.path.join(ROOT, "fortran", "specfab_b200.f90")).read()
+    bound = sorted(set(re.findall(r"bind\(c,\s*name='(sfb_[A-Za-z0-9_]+)'\)", src)))
+    names = declared_functions()
+    assert len(bound) >= 10
+    for nm in bound:
+        assert nm in names, "fortran shim binds an undeclared symbol " + nm
+    for nm in ("sfb_init", "sfb_step_arr", "sfb_step_rnlm_arr", "sfb_Eij_tranisotropic_arr"):
+        assert nm in bound

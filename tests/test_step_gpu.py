@@ -270,3 +270,65 @@ def test_full_form_kernels_agree_with_the_defaults(L, terms):
         assert relerr_nodes(got, ref).max() < TOL_STEP
     finally:
         _lib.load().sfb_set_variant(0)
+
+
+# --------------------------------------------------------------------------------------------------
+# reduced-form states (sfb_step_rnlm_arr): rows m >= 0 in, rows m >= 0 out  (src/reducedform.f90:160-187)
+# --------------------------------------------------------------------------------------------------
+def oracle_rnlm_index(L):
+    """positions of the m >= 0 coefficients in nlm, in rnlm order (l ascending, m = 0..l)"""
+    lm = [(l, m) for l in range(0, L + 1, 2) for m in range(-l, l + 1)]
+    return [lm.index((l, m)) for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+
+
+@pytest.mark.parametrize("L,terms", [(4, ("lrot", "reg")), (4, ("lrot", "ddrx", "reg")), (6, ("lrot", "ddrx", "reg")), (8, ("lrot", "reg")),
+                                     (8, ("lrot", "ddrx", "reg")), (10, ("lrot", "reg")), (12, ("lrot", "ddrx", "cdrx", "reg")),
+                                     (16, ("lrot", "reg")), (20, ("lrot", "ddrx", "cdrx", "reg"))])
+@pytest.mark.parametrize("scheme", ["euler", "rk4"])
+def test_step_on_reduced_form_states(L, terms, scheme):
+    """step_rnlm_arr == nlm_to_rnlm(step_arr(rnlm_to_nlm(rnlm))) bit for bit (the same arithmetic on the same rows), and
+    within 1e-12 of the oracle's full-form step; ragged batch (tile edges), host and device entry points."""
+    import torch
+    import specfab_b200 as sf
+    if L not in built_L():
+        pytest.skip("L not built")
+    lm, n = sf.init(L)
+    N = 77
+    x = random_states(L, N, 5 + L, True)
+    ug, tau = random_ugrad(N, 6), random_tau(N, 7)
+    kw = dict(dt=2e-3, Gamma0=3.0, Lambda=0.7, terms=terms, scheme=scheme)
+    idx = oracle_rnlm_index(L)
+    r = sf.rnlm_len()
+    assert r == len(idx) == (L + 2) ** 2 // 4
+    rx = sf.nlm_to_rnlm_arr(x)
+    assert np.array_equal(rx, x[:, idx])
+    full = sf.step_arr(x, ug, tau, **kw)
+    got = sf.step_rnlm_arr(rx, ug, tau, **kw)
+    assert got.shape == (N, r)
+    assert np.array_equal(got, full[:, idx]), "reduced-form step differs from the m >= 0 rows of the full-form step"
+    assert np.array_equal(sf.rnlm_to_nlm_arr(got), full)
+    k = N if L <= 12 else 10           # the pure-Python oracle is slow at large L
+    ref = oracle_steps(L, x[:k], ug[:k], tau[:k], scheme, 1, dt=2e-3, Gamma0=3.0, Lambda=0.7, use_ddrx="ddrx" in terms, use_cdrx="cdrx" in terms)
+    assert relerr_nodes(got[:k], ref[:, idx]).max() < TOL_STEP
+    # device-resident entry point, three sub-steps, in place
+    d = torch.from_numpy(np.ascontiguousarray(rx.T)).cuda()
+    sf.step_rnlm_arr_dev(d, sf.layout_mat(torch.from_numpy(ug).cuda()), sf.layout_mat(torch.from_numpy(tau).cuda()), nsteps=3, **kw)
+    full3 = sf.step_arr(x, ug, tau, nsteps=3, **kw)
+    assert np.array_equal(d.cpu().numpy().T, full3[:, idx])
+
+
+def test_reduced_form_step_errors_and_empty():
+    import specfab_b200 as sf
+    L = 8
+    lm, n = sf.init(L)
+    r = sf.rnlm_len()
+    assert sf.step_rnlm_arr(np.zeros((0, r), complex), np.zeros((0, 3, 3)), dt=0.1).shape == (0, r)
+    with pytest.raises(ValueError):
+        sf.step_rnlm_arr(np.zeros((3, n), complex), np.zeros((3, 3, 3)), dt=0.1)      # full-form array handed to the reduced entry
+    from specfab_b200 import _lib
+    _lib.load().sfb_set_variant(40)        # full-form kernels have no reduced I/O: must be refused, not silently wrong
+    try:
+        with pytest.raises(sf.SpecfabB200Error):
+            sf.step_rnlm_arr(sf.nlm_to_rnlm_arr(random_states(L, 4, 1, True)), random_ugrad(4, 2), dt=1e-3)
+    finally:
+        _lib.load().sfb_set_variant(0)

@@ -66,6 +66,16 @@ if __name__ == "__main__":
     if which == "8x":       # headline kernels only (L=8, LROT+REG)
         run(8, 1_000_000, ("lrot", "reg"), "rk4", V, steps=20)
         run(8, 1_000_000, ("lrot", "reg"), "euler", V, steps=20)
+    if which == "dd":       # DDRX kernels L = 6..12
+        run(8, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=20)
+        run(8, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V, steps=10)
+        run(6, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=20)
+        run(6, 1_000_000, ("lrot", "ddrx", "reg"), "rk4", V, steps=10)
+        run(10, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=10)
+        run(12, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=10)
+    if which == "loop":     # reduced loop kernels
+        run(12, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=10)
+        run(20, 300_000, ("lrot", "ddrx", "cdrx", "reg"), "euler", V, steps=10)
     if which == "4r":       # two-lane reduced kernels (L = 6, 8 with DDRX)
         for L in (8, 6):
             run(L, 1_000_000, ("lrot", "ddrx", "reg"), "euler", V, steps=20)
