@@ -67,7 +67,8 @@ EXP = {
     # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
-    # tiles or per-block lock step (0.73-0.75 ms, same as the default)
+    # tiles or per-block lock step (0.73-0.75 ms, same as the default); "+nofb" (no general-state fallback call in the kernel:
+    # no spills, L = 8 RK4 0.555 -> 0.531 ms) -- the measure of what moving the fallback to a second launch could gain
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
@@ -195,6 +196,8 @@ def generate(Ls):
                     cw = max([int(x[2:]) for x in parts[1:] if x.startswith("cw")] + [1])
                     if cw > 1:                     # "+cwN": N independent one-warp tiles per CTA (MINB then counts CTAs of N warps)
                         tab = "#define SFB_CW %d\n" % cw + tab
+                    if "nofb" in parts[1:]:        # experiment: no general-state fallback (traps)
+                        tab = "#define SFB_NOFB 1\n" + tab
                     if "n0" in parts[1:]:          # "+n0": n0 loaded from global in every stage (Horner kernels), no selects
                         tab = "#define SFB_N0ALL_REQ 1\n" + tab
                     if "a32" in parts[1:]:         # "+a32": 32-bit row strides + explicit global loads/stores in the row finalisation

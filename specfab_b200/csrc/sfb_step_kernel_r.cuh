@@ -263,8 +263,12 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
     } else if ((kCW > 1 && !kLS) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad) != 0)) {     // also orders the forcing preparation before the stages
         if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
         SFB_TILE_SYNC();
+#ifdef SFB_NOFB
+        __trap();                       // experiment only: how much does the presence of the fallback call cost the reduced path?
+#else
         full_tile(P, node0, smem_raw);
         if (node0 + kTN < P.N) full_tile(P, node0 + kTN, smem_raw);
+#endif
         return;
     }
 
