@@ -68,7 +68,10 @@ EXP = {
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
     # tiles or per-block lock step (0.73-0.75 ms, same as the default); "+nofb" (no general-state fallback call in the kernel:
-    # no spills, L = 8 RK4 0.555 -> 0.531 ms) -- the measure of what moving the fallback to a second launch could gain
+    # no spills, L = 8 RK4 0.555 -> 0.531 ms) -- the measure of what moving the fallback to a second launch could gain;
+    # L2 bulk prefetch of the tile K CTAs further down the grid (K = 100..888: 0.555 -> 0.555..0.617 ms); the symmetry test folded
+    # into stage 0 (mirror rows loaded in place of the redundant stage-0 n0 loads: 0.555 -> 0.729 ms, they come from DRAM inside
+    # short m blocks); without any test the kernel would run at 0.485 ms (profiles/r01_notes.md)
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;

@@ -8,7 +8,7 @@ import specfab_b200 as sf
 from specfab_b200 import _lib
 
 
-def run(L, N, terms, scheme, variants, steps=10, physical=True):
+def run(L, N, terms, scheme, variants, steps=10, physical=True, reduced=False):
     lm, n = sf.init(L)
     g = torch.Generator(device="cuda").manual_seed(1)
     nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
@@ -21,6 +21,11 @@ def run(L, N, terms, scheme, variants, steps=10, physical=True):
             nlm[base] = nlm[base].real.to(torch.complex128)
             for m in range(1, l + 1):
                 nlm[base - m] = (-1) ** m * nlm[base + m].conj()
+    stepf = sf.step_arr_dev
+    if reduced:           # state in reduced form (rows m >= 0), step_rnlm_arr_dev
+        rows = [l * (l + 1) // 2 + m for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+        nlm = nlm[torch.tensor(rows, device="cuda")].contiguous()
+        stepf = sf.step_rnlm_arr_dev
     ug = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
     tau = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
     tau = (tau + tau.permute(1, 0, 2)) / 2
@@ -35,7 +40,7 @@ def run(L, N, terms, scheme, variants, steps=10, physical=True):
         out = torch.empty_like(nlm)
         try:
             for _ in range(3):
-                sf.step_arr_dev(nlm, ug, tau, out=out, **kw)
+                stepf(nlm, ug, tau, out=out, **kw)
         except Exception as ex:
             print(json.dumps(dict(L=L, variant=v, error=str(ex)[:120])), flush=True)
             continue
@@ -43,7 +48,7 @@ def run(L, N, terms, scheme, variants, steps=10, physical=True):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            sf.step_arr_dev(nlm, ug, tau, out=out, **kw)
+            stepf(nlm, ug, tau, out=out, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -53,7 +58,7 @@ def run(L, N, terms, scheme, variants, steps=10, physical=True):
         k = info[key]
         nst = 4 if scheme == "rk4" else 1
         rate = N / (ms * 1e-3)
-        print(json.dumps(dict(L=L, terms="+".join(terms), scheme=scheme, physical=physical, variant=v, roles=k["roles"], tile=k["tile"], ms=round(ms, 4),
+        print(json.dumps(dict(L=L, terms="+".join(terms), scheme=scheme, physical=physical, reduced=reduced, variant=v, roles=k["roles"], tile=k["tile"], ms=round(ms, 4),
                               rate=round(rate / 1e6, 1), tflops=round(2 * k["dfma_per_node_rhs"] * nst * rate / 1e12, 2), diff_vs_v0=err)), flush=True)
     _lib.load().sfb_set_variant(0)
 
@@ -63,6 +68,9 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if len(sys.argv) > 2:
         V = [int(x) for x in sys.argv[2].split(",")]
+    if which == "8xr":      # headline kernels on reduced-form states
+        run(8, 1_000_000, ("lrot", "reg"), "rk4", V, steps=20, reduced=True)
+        run(8, 1_000_000, ("lrot", "reg"), "euler", V, steps=20, reduced=True)
     if which == "8x":       # headline kernels only (L=8, LROT+REG)
         run(8, 1_000_000, ("lrot", "reg"), "rk4", V, steps=20)
         run(8, 1_000_000, ("lrot", "reg"), "euler", V, steps=20)
