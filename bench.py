@@ -335,7 +335,19 @@ def main():
     per_gpu_rate = N / (ms * 1e-3)
     fpk, fsrc = fp64_peak()
     hpk, hsrc = hbm_peak()
-    ach_tf = 2.0 * info["dfma_per_node_rhs"] * nst * per_gpu_rate / 1e12
+    # FP64 work per node-step, in FP64-pipe instruction slots (a DFMA, DMUL or DADD occupies the pipe alike; the measured
+    # peak is a DFMA chain = 2 flop per slot).  Counted conservatively: min(instructions the kernel EXECUTES -- ncu,
+    # profiles/fp64_ops.json; the compiler drops e.g. the imaginary parts of the m = 0 rows --, the code generator's count
+    # of the factorised algorithm -- which excludes the zero padding the table-driven loop kernels execute).
+    nominal = info["dfma_per_node_rhs"] * nst
+    ops = None
+    try:
+        ops = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json"))).get({2: "cfg2", 3: "cfg3", 4: "cfg4", 5: "cfg5_step"}[cfg])
+    except Exception:
+        pass
+    executed = (ops["dfma"] + ops["dmul"] + ops["dadd"]) if ops else None
+    slots = min(executed, nominal) if executed else nominal
+    ach_tf = 2.0 * slots * per_gpu_rate / 1e12
     ach_gb = alg_bytes_per_node_step(n, terms, eij) * per_gpu_rate / 1e9
     fp_frac, hbm_frac = ach_tf / fpk, ach_gb / hpk
     traffic = None
@@ -350,13 +362,18 @@ def main():
         roof = {"bound": "hbm", "achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc}
     reduced = info["roles"] >= 1 and info["tile"] == 32 and any(
         k["L"] == L and k["ddrx"] == info["ddrx"] and k["variant"] == 40 for k in sf.build_info()["step_kernels"])
-    full = [k for k in sf.build_info()["step_kernels"] if k["L"] == L and k["ddrx"] == info["ddrx"] and k["variant"] == 40]
     roof.update({"traffic": traffic,
                  "kernel": "%s (L=%d, %s, %s)" % ("step_kernel_r" if reduced else "step_kernel", L, "+".join(terms), scheme),
                  "form": ("reduced: only the rows m >= 0 are computed (real-ODF symmetry of every 32-node tile verified in the kernel, "
                           "full-form fallback otherwise; SURVEY.md 8d: flop counts scaled accordingly)") if reduced else "full",
-                 "flops_per_node_step_executed": 2 * info["dfma_per_node_rhs"] * nst,
-                 "flops_per_node_step_full_form": (2 * full[0]["dfma_per_node_rhs"] * nst) if full else None,
+                 "fp64_accounting": "achieved = 2 flop x FP64-pipe instruction slots per node-step x node rate (DFMA-equivalent: DFMA, DMUL and "
+                                    "DADD occupy the pipe alike and the measured peak is a DFMA chain); slots = min(executed per ncu, "
+                                    "code generator's count); cross-check: ncu sm__pipe_fp64_cycles_active of the same kernel = "
+                                    "%s %% (profiles/fp64_ops.json)" % (ops["pipe_fp64_pct"] if ops else "n/a"),
+                 "fp64_slots_per_node_step": slots,
+                 "fp64_ops_executed_per_node_step": ({"dfma": ops["dfma"], "dmul": ops["dmul"], "dadd": ops["dadd"]} if ops else None),
+                 "flops_executed_per_node_step": (2 * ops["dfma"] + ops["dmul"] + ops["dadd"]) if ops else None,
+                 "fp64_slots_codegen_per_node_step": nominal,
                  "alg_bytes_per_node_step": alg_bytes_per_node_step(n, terms, eij),
                  "hbm": {"achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc},
                  "fp64": {"achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc},
@@ -383,7 +400,8 @@ def main():
             for sc in ("rk4", "euler"):
                 m3, _, _, fin3 = time_config(sf, torch, cfg, N, rank, 10, 3, reduced=True, scheme=sc)
                 rr[sc] = {"ms_per_step": m3, "node_updates_per_s": N / (m3 * 1e-3), "alg_bytes_per_node_step": 32 * r + 72,
-                          "hbm_gbs_alg": (32 * r + 72) * N / (m3 * 1e-3) / 1e9, "finite": fin3}
+                          "hbm_gbs_alg": (32 * r + 72) * N / (m3 * 1e-3) / 1e9, "hbm_frac": (32 * r + 72) * N / (m3 * 1e-3) / 1e9 / hpk,
+                          "fp64_frac": 2.0 * (slots / nst) * (4 if sc == "rk4" else 1) * N / (m3 * 1e-3) / 1e12 / fpk, "finite": fin3}
             if not eij:
                 sec3, h3, d3 = time_e2e(sf, torch, cfg, N, rank, 3, 1, reduced=True)
                 rr["e2e"] = {"value": N / sec3, "unit": "node-updates/s", "h2d_bytes_per_step": h3, "d2h_bytes_per_step": d3,
@@ -415,6 +433,12 @@ def main():
             me = a.elapsed_time(b) / 10
             extra["eij"] = {"workload": "stand-alone a2 -> eigenframe -> Eij_tranisotropic, 4e6 nodes, L=8", "ms": me,
                             "eij_evals_per_s": Ne / (me * 1e-3), "hbm_gbs_alg": 288 * Ne / (me * 1e-3) / 1e9}
+            try:
+                eo_ = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json")))["eij"]
+                sl = eo_["dfma"] + eo_["dmul"] + eo_["dadd"]
+                extra["eij"].update({"fp64_slots_per_eval": sl, "fp64_frac": 2.0 * sl * Ne / (me * 1e-3) / 1e12 / fpk})
+            except Exception:
+                pass
             del st, ugd, eo
         except Exception as ex:   # noqa
             extra["eij"] = {"error": str(ex)[:200]}

@@ -23,7 +23,12 @@ if os.environ.get("SFB_GENERAL_STATES", "0") != "1":      # real-ODF symmetry (w
 ug = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
 tau = torch.randn((3, 3, N), dtype=torch.float64, device="cuda", generator=g)
 tau = (tau + tau.permute(1, 0, 2)) / 2
+stepf = sf.step_arr_dev
+if os.environ.get("SFB_RNLM", "0") == "1":               # state in reduced form (rows m >= 0): step_rnlm_arr_dev
+    rows = [l * (l + 1) // 2 + m for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+    nlm = nlm[torch.tensor(rows, device="cuda")].contiguous()
+    stepf = sf.step_rnlm_arr_dev
 out = torch.empty_like(nlm)
 for _ in range(steps):
-    sf.step_arr_dev(nlm, ug, tau, out=out, dt=1e-3, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
+    stepf(nlm, ug, tau, out=out, dt=1e-3, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
 torch.cuda.synchronize()
