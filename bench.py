@@ -410,6 +410,34 @@ def main():
             extra["rnlm"] = rr
         except Exception as ex:   # noqa
             extra["rnlm"] = {"error": str(ex)[:200]}
+        # BASELINE config 5 (FE coupling: step + eigenframe + Eij per node) on a field kept in reduced form
+        try:
+            L5, n5, t5, s5, _, d5 = CONFIGS[5]
+            sf.init(L5)
+            u5, tt5 = synth_forcing(n5, 20260817 + rank)
+            ug5 = torch.from_numpy(np.ascontiguousarray(u5.transpose(2, 1, 0))).cuda()
+            ta5 = torch.from_numpy(np.ascontiguousarray(tt5.transpose(2, 1, 0))).cuda()
+            st5 = torch.zeros((sf.rnlm_len(), n5), dtype=torch.complex128, device="cuda")
+            st5[0] = 1 / np.sqrt(4 * np.pi)
+            kw5 = dict(dt=DT, Gamma0=4.0, Lambda=1.0, terms=t5, scheme=s5)
+            for _ in range(50):
+                sf.step_rnlm_arr_dev(st5, ug5, ta5, **kw5)
+            for _ in range(3):
+                sf.step_moments_Eij_rnlm_arr_dev(st5, ug5, ta5, GRAIN, ALPHA, 1, want_frame=True, **kw5)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                sf.step_moments_Eij_rnlm_arr_dev(st5, ug5, ta5, GRAIN, ALPHA, 1, want_frame=True, **kw5)
+            b.record()
+            torch.cuda.synchronize()
+            m5 = a.elapsed_time(b) / 10
+            extra["cfg5_rnlm"] = {"workload": d5 + ", state in reduced form (sfb_step_moments_Eij_rnlm_arr_dev)", "nodes": n5, "ms_per_step": m5,
+                                  "node_updates_per_s": n5 / (m5 * 1e-3), "finite": bool(torch.isfinite(torch.view_as_real(st5)).all().item())}
+            del st5, ug5, ta5
+            sf.init(L)
+        except Exception as ex:   # noqa
+            extra["cfg5_rnlm"] = {"error": str(ex)[:200]}
         # stand-alone Eij evals/s (a2 -> eigenframe -> 6 Sachs/Taylor factors per node)
         try:
             lm, n8 = sf.init(8)

@@ -101,6 +101,16 @@ int sfb_step_moments_Eij_arr_dev(const double* nlm_in, double* nlm_out, int64_t 
                                  const double* Eij_grain, double alpha, int n_grain,
                                  double* Eij, double* a2, double* a4, double* ei, double* lami, int32_t* status, void* stream);
 
+/* The FE time step for couplers that keep the state in reduced form (src/specfabpy/fenics/CPO.py): step_rnlm, then a2
+ * (optional), the a2 eigenframe (optional) and Eij of the new state, all read from the m >= 0 rows.  n_grain = 1 or -3.
+ * sfb_Eij_eigenframe_rnlm_arr_dev is the second half alone (a2 -> eigenframe -> Eij of a reduced-form state). */
+int sfb_Eij_eigenframe_rnlm_arr_dev(const double* rnlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                                    double* Eij, double* a2, double* ei, double* lami, int32_t* status, void* stream);
+int sfb_step_moments_Eij_rnlm_arr_dev(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                                      const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t, const sfb_step_opts* opts,
+                                      const double* Eij_grain, double alpha, int n_grain,
+                                      double* Eij, double* a2, double* ei, double* lami, int32_t* status, void* stream);
+
 /* a2(nlm) -> (N,3,3)                         src/specfabpy.f90:583-590, src/moments.f90:37-44 */
 int sfb_a2_arr(const double* nlm, int64_t N, int64_t ld, double* a2);
 int sfb_a2_arr_dev(const double* nlm, int64_t N, int64_t ld, double* a2, void* stream);

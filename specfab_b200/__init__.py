@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "dndt_LATROT", "dndt_DDRX", "dndt_CDRX", "dndt_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
-           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "build_info", "layout_nlm", "layout_mat",
+           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "step_moments_Eij_rnlm_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "step_moments_Eij_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
@@ -624,6 +624,43 @@ def _step_dev(reduced, nlm, ugrad, tau, out, dt, iota, zeta, nu, Gamma0, Lambda,
     _lib.check((lib.sfb_step_rnlm_arr_dev if reduced else lib.sfb_step_arr_dev)(nlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
                                     tau.data_ptr() if tau is not None else None, N, C.byref(o), _stream_ptr()))
     return out
+
+
+def step_moments_Eij_rnlm_arr_dev(rnlm, ugrad, tau, Eij_grain, alpha, n_grain, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0,
+                                  Gamma0=0.0, Lambda=0.0, terms=("lrot", "reg"), scheme="euler", nsteps=1, want_a2=False,
+                                  want_frame=False, step=True):
+    """step_moments_Eij_arr_dev for a resident field kept in REDUCED form: rnlm (rnlm_len, N) complex128 CUDA tensor (rows
+    m >= 0, see step_rnlm_arr).  step=False: only a2 / eigenframe / Eij of the given state.  n_grain = 1 or -3.
+    Returns a dict with 'rnlm', 'Eij' (6,N) and, when asked for, 'a2' (3,3,N), 'ei' (3,3,N), 'lami' (3,N)."""
+    import torch
+    _need_init()
+    r = rnlm_len()
+    if rnlm.dtype != torch.complex128 or not rnlm.is_cuda or not rnlm.is_contiguous() or rnlm.shape[0] != r:
+        raise ValueError("rnlm must be a contiguous CUDA complex128 tensor of shape (rnlm_len, N)")
+    N = rnlm.shape[1]
+    out = rnlm if (out is None or not step) else out
+    dev = rnlm.device
+    res = {"rnlm": out, "Eij": torch.empty((6, N), dtype=torch.float64, device=dev)}
+    if want_a2:
+        res["a2"] = torch.empty((3, 3, N), dtype=torch.float64, device=dev)
+    if want_frame:
+        res["ei"] = torch.empty((3, 3, N), dtype=torch.float64, device=dev)
+        res["lami"] = torch.empty((3, N), dtype=torch.float64, device=dev)
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    if g.shape != (2,):
+        raise ValueError("Eij_grain must have 2 entries (Emm, Emt)")
+    ptr = lambda k: res[k].data_ptr() if k in res else None
+    lib = _lib.load()
+    if step:
+        o = _opts(dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, None, None)
+        _lib.check(lib.sfb_step_moments_Eij_rnlm_arr_dev(rnlm.data_ptr(), out.data_ptr(), N, N, N, ugrad.data_ptr(), N,
+                                                         tau.data_ptr() if tau is not None else None, N, C.byref(o),
+                                                         g.ctypes.data, float(alpha), int(n_grain), res["Eij"].data_ptr(),
+                                                         ptr("a2"), ptr("ei"), ptr("lami"), None, _stream_ptr()))
+    else:
+        _lib.check(lib.sfb_Eij_eigenframe_rnlm_arr_dev(rnlm.data_ptr(), N, N, g.ctypes.data, float(alpha), int(n_grain),
+                                                       res["Eij"].data_ptr(), ptr("a2"), ptr("ei"), ptr("lami"), None, _stream_ptr()))
+    return res
 
 
 def step_moments_Eij_arr_dev(nlm, ugrad, tau, Eij_grain, alpha, n_grain, out=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0,

@@ -72,6 +72,9 @@ SIGNATURES = {
     "sfb_Eij_orthotropic_arr_dev": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
     "sfb_Eij_eigenframe_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P]),
     "sfb_Eij_eigenframe_arr_dev": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P]),
+    "sfb_Eij_eigenframe_rnlm_arr_dev": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "sfb_step_moments_Eij_rnlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, C.c_double, C.c_int,
+                                                    _P, _P, _P, _P, _P, _P]),
     "sfb_M_LROT_arr": (C.c_int, [_P, _P, _I64, C.c_double, C.c_double, _P]),
     "sfb_M_LROT_arr_dev": (C.c_int, [_P, _P, _I64, _I64, C.c_double, C.c_double, _P, _P]),
     "sfb_M_DDRX_src_arr": (C.c_int, [_P, _I64, _P]),

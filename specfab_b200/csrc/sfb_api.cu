@@ -18,10 +18,10 @@ void sfb_ops_release();
 cudaError_t sfb_launch_bounds(const double2* in, double2* out, long long N, long long ldi, long long ldo, int n, cudaStream_t st);
 cudaError_t sfb_launch_reduced(int to_reduced, const double2* src, double2* dst, long long N, long long lds, long long ldd, int L,
                                cudaStream_t st);
-cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
+cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st, int red = 0);
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
-                           long long ldo, cudaStream_t st);
+                           long long ldo, cudaStream_t st, int red = 0);
 cudaError_t sfb_launch_a6(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eij3(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                             long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
@@ -40,7 +40,7 @@ cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2*
                                 const double* Eij_grain, int n_grain, double* Eij, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
-                           int* status, cudaStream_t st);
+                           int* status, cudaStream_t st, int red = 0);
 
 struct SfbStepEntry {
     int L, ddrx, variant, R, TN, dfma_node;
@@ -450,8 +450,10 @@ int sfb_Eij_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, cons
     if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
     if (N == 0) return SFB_OK;
     if (!e1 || !e2 || !e3 || !Eij) return fail(SFB_EINVAL, "null array");
-    CK((n_grain == 3 ? sfb_launch_eij3 : sfb_launch_eij)(reinterpret_cast<const double2*>(nlm), N, ld, e1, e2, e3, N, K, Eij, N, nullptr,
-                                                         nullptr, status, (cudaStream_t)stream));
+    if (n_grain == 3)
+        CK(sfb_launch_eij3(reinterpret_cast<const double2*>(nlm), N, ld, e1, e2, e3, N, K, Eij, N, nullptr, nullptr, status, (cudaStream_t)stream));
+    else
+        CK(sfb_launch_eij(reinterpret_cast<const double2*>(nlm), N, ld, e1, e2, e3, N, K, Eij, N, nullptr, nullptr, status, (cudaStream_t)stream));
     return SFB_OK;
 }
 int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
@@ -615,18 +617,41 @@ int sfb_Eij_orthotropic_arr(const double* nlm_1, const double* nlm_2, const doub
     CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }
-int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
-                               double* Eij, double* ei, double* lami, int32_t* status, void* stream) {
+// red = 1: the state array is in reduced form (rows m >= 0; n' = 1 and -3 only: the n' = 3 closure reads rows up to l = 8)
+static int eij_eigenframe_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                              double* Eij, double* ei, double* lami, int32_t* status, void* stream, int red) {
     int rc = basic_check(nlm, N, ld);
     if (rc) return rc;
     sfb::EijCoef K;
     if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
+    if (red && n_grain == 3) return fail(SFB_EINVAL, "reduced-form states: n_grain must be 1 or -3");
     if (N == 0) return SFB_OK;
     if (!Eij) return fail(SFB_EINVAL, "null array");
     if ((ei == nullptr) != (lami == nullptr)) return fail(SFB_EINVAL, "ei and lami must both be given or both be NULL");
-    CK((n_grain == 3 ? sfb_launch_eij3 : sfb_launch_eij)(reinterpret_cast<const double2*>(nlm), N, ld, nullptr, nullptr, nullptr, 0, K, Eij,
-                                                         N, ei, lami, status, (cudaStream_t)stream));
+    if (n_grain == 3)
+        CK(sfb_launch_eij3(reinterpret_cast<const double2*>(nlm), N, ld, nullptr, nullptr, nullptr, 0, K, Eij, N, ei, lami, status, (cudaStream_t)stream));
+    else
+        CK(sfb_launch_eij(reinterpret_cast<const double2*>(nlm), N, ld, nullptr, nullptr, nullptr, 0, K, Eij, N, ei, lami, status, (cudaStream_t)stream, red));
     return SFB_OK;
+}
+int sfb_Eij_eigenframe_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                               double* Eij, double* ei, double* lami, int32_t* status, void* stream) {
+    return eij_eigenframe_dev(nlm, N, ld, Eij_grain, alpha, n_grain, Eij, ei, lami, status, stream, 0);
+}
+int sfb_Eij_eigenframe_rnlm_arr_dev(const double* rnlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
+                                    double* Eij, double* a2, double* ei, double* lami, int32_t* status, void* stream) {
+    int rc = basic_check(rnlm, N, ld);
+    if (rc) return rc;
+    if (a2 && N > 0) CK(sfb_launch_a2(reinterpret_cast<const double2*>(rnlm), N, ld, a2, N, (cudaStream_t)stream, 1));
+    return eij_eigenframe_dev(rnlm, N, ld, Eij_grain, alpha, n_grain, Eij, ei, lami, status, stream, 1);
+}
+int sfb_step_moments_Eij_rnlm_arr_dev(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
+                                      const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t, const sfb_step_opts* opts,
+                                      const double* Eij_grain, double alpha, int n_grain,
+                                      double* Eij, double* a2, double* ei, double* lami, int32_t* status, void* stream) {
+    int rc = sfb_step_rnlm_arr_dev(rnlm_in, rnlm_out, N, ld_in, ld_out, ugrad, ld_u, tau, ld_t, opts, stream);
+    if (rc) return rc;
+    return sfb_Eij_eigenframe_rnlm_arr_dev(rnlm_out, N, ld_out, Eij_grain, alpha, n_grain, Eij, a2, ei, lami, status, stream);
 }
 int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,
                            double* Eij, double* ei, double* lami, int32_t* status) {

@@ -9,13 +9,14 @@ constexpr int kBlock = 128;
 using sfb::load_m_ge0;
 using sfb::a2_from;
 
+// red: the state array is in reduced form (see load_m_ge0)
 __global__ void __launch_bounds__(kBlock) a2_kernel(const double2* __restrict__ nlm, long long N, long long ld,
-                                                    double* __restrict__ out, long long ldo) {
+                                                    double* __restrict__ out, long long ldo, int red) {
     const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (p >= N) return;
     double2 n00 = nlm[p], n2[3];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];
+    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)((red ? 1 : 3) + m) * ld + p];
     double a[3][3];
     a2_from(n00, n2, a);
 #pragma unroll
@@ -54,14 +55,14 @@ __global__ void __launch_bounds__(kBlock) a4_kernel(const double2* __restrict__ 
 // eig(nlm) (mode 0, src/frames.f90:14-22) or eigframe(M, plane) (mode 1, src/frames.f90:24-60)
 __global__ void __launch_bounds__(kBlock) eig_kernel(const double2* __restrict__ nlm, const double* __restrict__ M,
                                                      long long N, long long ld, int plane,
-                                                     double* __restrict__ ei, double* __restrict__ lami, long long ldo) {
+                                                     double* __restrict__ ei, double* __restrict__ lami, long long ldo, int red) {
     const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (p >= N) return;
     double a[3][3];
     if (nlm) {
         double2 n00 = nlm[p], n2[3];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];
+        for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)((red ? 1 : 3) + m) * ld + p];
         a2_from(n00, n2, a);
     } else {
 #pragma unroll
@@ -87,11 +88,11 @@ __global__ void __launch_bounds__(kBlock, MB) eij_kernel(const double2* __restri
                                                      const double* __restrict__ e3, long long lde, sfb::EijCoef K,
                                                      double* __restrict__ Eij, long long ldo,
                                                      double* __restrict__ ei_out, double* __restrict__ lam_out,
-                                                     int* __restrict__ status) {
+                                                     int* __restrict__ status, int red) {
     const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (p >= N) return;
     double2 n00, n2[3], n4[5];
-    load_m_ge0(nlm, ld, p, n00, n2, n4);
+    load_m_ge0(nlm, ld, p, n00, n2, n4, red);
     double e[3][3];
     if (e1) {
 #pragma unroll
@@ -167,8 +168,8 @@ inline unsigned nblk(long long N) { return (unsigned)((N + kBlock - 1) / kBlock)
 
 }  // namespace
 
-cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st) {
-    if (N > 0) a2_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, out, ldo);
+cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st, int red) {
+    if (N > 0) a2_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, out, ldo, red);
     return cudaGetLastError();
 }
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st) {
@@ -176,20 +177,20 @@ cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double*
     return cudaGetLastError();
 }
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
-                           long long ldo, cudaStream_t st) {
-    if (N > 0) eig_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, M, N, ld, plane, ei, lami, ldo);
+                           long long ldo, cudaStream_t st, int red) {
+    if (N > 0) eig_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, M, N, ld, plane, ei, lami, ldo, red);
     return cudaGetLastError();
 }
 cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
-                           int* status, cudaStream_t st) {
+                           int* status, cudaStream_t st, int red) {
     static int mb = 0;
     // 4 CTAs of 128 threads per SM (128 registers, a few spills) beats 2 x 255 registers: the kernel is FP64-latency bound
     if (!mb) { const char* ev = getenv("SFB_EIJ_MB"); mb = ev ? atoi(ev) : 4; }
     if (N > 0) {
-        if (mb == 3) eij_kernel<3><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
-        else if (mb == 4) eij_kernel<4><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
-        else eij_kernel<2><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status);
+        if (mb == 3) eij_kernel<3><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status, red);
+        else if (mb == 4) eij_kernel<4><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status, red);
+        else eij_kernel<2><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status, red);
     }
     return cudaGetLastError();
 }

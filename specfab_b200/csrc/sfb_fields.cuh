@@ -152,13 +152,16 @@ __device__ __forceinline__ void eigframe(const double m[3][3], int plane, double
 }
 
 // ---- node loads / a2 shared by the field kernels
+// red = 0: full nlm array (n_2^m at 0-based row 3+m, n_4^m at 10+m); red = 1: reduced form rnlm (rows m >= 0 only,
+// src/reducedform.f90:160-187: n_2^m at row 1+m, n_4^m at 4+m)
 __device__ __forceinline__ void load_m_ge0(const double2* __restrict__ nlm, long long ld, long long p,
-                                           double2& n00, double2 n2[3], double2 n4[5]) {
+                                           double2& n00, double2 n2[3], double2 n4[5], int red = 0) {
+    const int r2 = red ? 1 : 3, r4 = red ? 4 : 10;
     n00 = nlm[p];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(3 + m) * ld + p];     // n_2^m at 0-based index 3+m
+    for (int m = 0; m < 3; ++m) n2[m] = nlm[(long long)(r2 + m) * ld + p];
 #pragma unroll
-    for (int m = 0; m < 5; ++m) n4[m] = nlm[(long long)(10 + m) * ld + p];    // n_4^m at 0-based index 10+m
+    for (int m = 0; m < 5; ++m) n4[m] = nlm[(long long)(r4 + m) * ld + p];
 }
 
 __device__ __forceinline__ void a2_from(double2 n00, const double2 n2[3], double a[3][3]) {

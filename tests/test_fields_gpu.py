@@ -400,3 +400,39 @@ def test_step_moments_Eij_one_call():
     assert np.array_equal(r["lami"].cpu().numpy().T, lami)
     assert np.array_equal(r["a2"].cpu().numpy().transpose(2, 1, 0), sf.a2_arr(y))
     assert np.array_equal(r["a4"].cpu().numpy().transpose(4, 3, 2, 1, 0), sf.a4_arr(y))
+
+
+@pytest.mark.parametrize("n_grain", [1, -3])
+def test_step_moments_Eij_on_reduced_form_states(n_grain):
+    """the FE time step on a field kept in reduced form (rows m >= 0): step_rnlm + a2 + eigenframe + Eij in one call ==
+    the full-form calls bit for bit, and within tolerance of the oracle; the fields-only variant; n' = 3 is refused"""
+    import torch
+    import specfab_b200 as sf
+    sf.init(L)
+    N = 150
+    x = evolved_states(N, 191)
+    ug, tau = random_ugrad(N, 192), random_tau(N, 193)
+    kw = dict(dt=3.912e-3, Gamma0=4.0, terms=("lrot", "ddrx", "reg"), scheme="rk4")
+    rx = sf.nlm_to_rnlm_arr(x)
+    d = torch.from_numpy(np.ascontiguousarray(rx.T)).cuda()
+    ugd, taud = sf.layout_mat(torch.from_numpy(ug).cuda()), sf.layout_mat(torch.from_numpy(tau).cuda())
+    r = sf.step_moments_Eij_rnlm_arr_dev(d, ugd, taud, GRAIN, ALPHA, n_grain, out=torch.empty_like(d), want_a2=True, want_frame=True, **kw)
+    torch.cuda.synchronize()
+    y = sf.step_arr(x, ug, tau, **kw)
+    assert np.array_equal(r["rnlm"].cpu().numpy().T, sf.nlm_to_rnlm_arr(y))
+    E, ei, lami = sf.Eij_eigenframe_arr(y, GRAIN, ALPHA, n_grain, return_frame=True)
+    assert np.array_equal(r["Eij"].cpu().numpy().T, E)
+    assert np.array_equal(r["lami"].cpu().numpy().T, lami)
+    assert np.array_equal(r["ei"].cpu().numpy().transpose(2, 1, 0), ei)
+    assert np.array_equal(r["a2"].cpu().numpy().transpose(2, 1, 0), sf.a2_arr(y))
+    # oracle on a few nodes (full-form arithmetic of the reference)
+    orc.init(L)
+    for p in range(0, N, 37):
+        ref = orc.step_rk4(x[p], 3.912e-3, ug[p], tau[p], Gamma0=4.0, use_ddrx=True)
+        Er = orc.Eij_tranisotropic(ref, ei[p, 0], ei[p, 1], ei[p, 2], GRAIN, ALPHA, n_grain)
+        assert np.abs(r["Eij"].cpu().numpy().T[p] / Er - 1).max() < 1e-9
+    # fields only, on the stepped state
+    f = sf.step_moments_Eij_rnlm_arr_dev(r["rnlm"], None, None, GRAIN, ALPHA, n_grain, want_a2=True, step=False)
+    assert np.array_equal(f["Eij"].cpu().numpy(), r["Eij"].cpu().numpy()) and np.array_equal(f["a2"].cpu().numpy(), r["a2"].cpu().numpy())
+    with pytest.raises(sf.SpecfabB200Error):
+        sf.step_moments_Eij_rnlm_arr_dev(r["rnlm"], None, None, GRAIN, ALPHA, 3, step=False)
