@@ -122,6 +122,11 @@ def test_config1_parcel_1000_euler_steps():
     orc.init(L)
     a2 = orc.a2(got[0])
     assert abs(np.trace(a2) - 1) < 1e-12 and a2[2, 2] > 0.8     # single maximum along z
+    # the same 1000 steps with the state kept in reduced form: identical rows, and still within tolerance of the oracle
+    idx = [l * (l + 1) // 2 + m for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+    rgot = sf.step_rnlm_arr(sf.nlm_to_rnlm_arr(x), ug, dt=dt, terms=("lrot", "reg"), nsteps=1000)
+    assert np.array_equal(rgot, got[:, idx])
+    assert relerr_nodes(rgot, ref[:, idx]).max() < TOL_1000
 
 
 def test_1000_steps_all_terms_rk4():
@@ -136,6 +141,9 @@ def test_1000_steps_all_terms_rk4():
     got = sf.step_arr(x, ug, tau, dt=dt, terms=("lrot", "ddrx", "cdrx", "reg"), scheme="rk4", nsteps=250, **kw)
     ref = oracle_steps(L, x, ug, tau, "rk4", 250, dt=dt, use_ddrx=True, use_cdrx=True, **kw)
     assert relerr_nodes(got, ref).max() < TOL_1000
+    idx = [l * (l + 1) // 2 + m for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+    rgot = sf.step_rnlm_arr(sf.nlm_to_rnlm_arr(x), ug, tau, dt=dt, terms=("lrot", "ddrx", "cdrx", "reg"), scheme="rk4", nsteps=250, **kw)
+    assert np.array_equal(rgot, got[:, idx])
 
 
 def test_empty_and_ragged_and_errors():
