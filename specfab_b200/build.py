@@ -72,7 +72,9 @@ EXP = {
     # L2 bulk prefetch of the tile K CTAs further down the grid (K = 100..888: 0.555 -> 0.555..0.617 ms); the symmetry test folded
     # into stage 0 (mirror rows loaded in place of the redundant stage-0 n0 loads: 0.555 -> 0.729 ms, they come from DRAM inside
     # short m blocks); without any test the kernel would run at 0.485 ms (profiles/r01_notes.md); global stores in a rolled
-    # epilogue loop instead of the unrolled stage body ("+ep": body 8 % shorter, L = 8 RK4 0.558 -> 0.573 ms, L = 10 0.949 -> 0.893 ms)
+    # epilogue loop instead of the unrolled stage body ("+ep": body 8 % shorter, L = 8 RK4 0.558 -> 0.573 ms, L = 10 0.949 -> 0.893 ms);
+    # mirror rows prefetched to L2 at the head of the tile and tested in the LAST stage next to the n0 re-reads, stores in an epilogue
+    # ("+lsym": 0.557 -> 0.663 ms)
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
