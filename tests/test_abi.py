@@ -69,3 +69,31 @@ def test_fortran_shim_binds_only_declared_symbols():
         assert nm in names, "fortran shim binds an undeclared symbol " + nm
     for nm in ("sfb_init", "sfb_step_arr", "sfb_step_rnlm_arr", "sfb_Eij_tranisotropic_arr"):
         assert nm in bound
+
+
+def test_compute_entry_points_refuse_to_run_uninitialised():
+    """without a device sfb_init fails, and every compute entry point must then return SFB_ENOINIT -- no crash, no CPU path"""
+    import ctypes as C
+    from specfab_b200 import _lib
+    lib = _lib.load()
+    if lib.sfb_device_count() > 0:
+        pytest.skip("device present: the library may be initialised by other tests")
+    assert lib.sfb_init(8) == _lib.SFB_ECUDA
+    o = _lib.StepOpts()
+    o.dt, o.terms, o.scheme, o.nsteps = 0.1, 1, 1, 1
+    buf = (C.c_double * 4096)()
+    p = C.cast(buf, C.c_void_p)
+    calls = [
+        lambda: lib.sfb_step_arr(p, p, 1, 1, p, None, C.byref(o)),
+        lambda: lib.sfb_step_rnlm_arr(p, p, 1, 1, p, None, C.byref(o)),
+        lambda: lib.sfb_step_arr_dev(p, p, 1, 1, 1, p, 1, None, 1, C.byref(o), None),
+        lambda: lib.sfb_step_rnlm_arr_dev(p, p, 1, 1, 1, p, 1, None, 1, C.byref(o), None),
+        lambda: lib.sfb_a2_arr(p, 1, 1, p),
+        lambda: lib.sfb_a4_arr(p, 1, 1, p),
+        lambda: lib.sfb_eig_arr(p, 1, 1, p, p),
+        lambda: lib.sfb_Eij_eigenframe_arr(p, 1, 1, p, 0.0125, 1, p, None, None, None),
+        lambda: lib.sfb_Eij_eigenframe_rnlm_arr_dev(p, 1, 1, p, 0.0125, 1, p, None, None, None, None, None),
+    ]
+    for f in calls:
+        assert f() == _lib.SFB_ENOINIT
+    assert b"sfb_init" in lib.sfb_last_error()
