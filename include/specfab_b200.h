@@ -216,6 +216,9 @@ int sfb_apply_bounds_arr(const double* nlm_in, double* nlm_out, int64_t N, int64
 int sfb_apply_bounds_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out, void* stream);
 /* reduced form of real-valued ODFs: rnlm(N, rnlm_len) holds the m >= 0 coefficients, (L+2)^2/4 of them
  *                                            src/specfabpy.f90:1039-1061, src/reducedform.f90:160-187 */
+/* apply_bounds on a reduced-form field, device pointers: what src/specfabpy/fenics/CPO.py:339-365 does per node through
+ * rnlm_to_nlm / apply_bounds / nlm_to_rnlm (same rescaling factors as sfb_apply_bounds_arr, bit for bit). */
+int sfb_apply_bounds_rnlm_arr_dev(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld_in, int64_t ld_out, void* stream);
 int sfb_rnlm_len(void);
 int sfb_nlm_to_rnlm_arr(const double* nlm, double* rnlm, int64_t N);
 int sfb_nlm_to_rnlm_arr_dev(const double* nlm, double* rnlm, int64_t N, int64_t ld_nlm, int64_t ld_rnlm, void* stream);

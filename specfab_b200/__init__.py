@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "dndt_LATROT", "dndt_DDRX", "dndt_CDRX", "dndt_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
-           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "step_moments_Eij_rnlm_arr_dev", "build_info", "layout_nlm", "layout_mat",
+           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "step_moments_Eij_rnlm_arr_dev", "apply_bounds_rnlm_arr_dev", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "step_moments_Eij_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
@@ -295,6 +295,19 @@ def apply_bounds_arr(nlm):
     N = x.shape[0]
     out = np.empty((N, n), dtype=np.complex128, order="F")
     _lib.check(_lib.load().sfb_apply_bounds_arr(x.ctypes.data, out.ctypes.data, N, N))
+    return out
+
+
+def apply_bounds_rnlm_arr_dev(rnlm, out=None):
+    """apply_bounds on a resident reduced-form field: rnlm (rnlm_len, N) complex128 CUDA tensor, in place by default
+    (what src/specfabpy/fenics/CPO.py:339-365 does per node; reference procedure src/dynamics.f90:530-557)."""
+    import torch
+    _need_init()
+    if rnlm.dtype != torch.complex128 or not rnlm.is_cuda or not rnlm.is_contiguous() or rnlm.shape[0] != rnlm_len():
+        raise ValueError("rnlm must be a contiguous CUDA complex128 tensor of shape (rnlm_len, N)")
+    out = rnlm if out is None else out
+    N = rnlm.shape[1]
+    _lib.check(_lib.load().sfb_apply_bounds_rnlm_arr_dev(rnlm.data_ptr(), out.data_ptr(), N, N, N, _stream_ptr()))
     return out
 
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sfb_build_info": (C.c_char_p, []),
     "sfb_step_arr": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(StepOpts)]),
     "sfb_step_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, C.POINTER(StepOpts), _P]),
+    "sfb_apply_bounds_rnlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "sfb_step_rnlm_arr": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(StepOpts)]),
     "sfb_step_rnlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, C.POINTER(StepOpts), _P]),
     "sfb_a2_arr": (C.c_int, [_P, _I64, _I64, _P]),

@@ -18,6 +18,7 @@ void sfb_ops_release();
 cudaError_t sfb_launch_bounds(const double2* in, double2* out, long long N, long long ldi, long long ldo, int n, cudaStream_t st);
 cudaError_t sfb_launch_reduced(int to_reduced, const double2* src, double2* dst, long long N, long long lds, long long ldd, int L,
                                cudaStream_t st);
+cudaError_t sfb_launch_bounds_rnlm(const double2* in, double2* out, long long N, long long ldi, long long ldo, int r, cudaStream_t st);
 cudaError_t sfb_launch_a2(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st, int red = 0);
 cudaError_t sfb_launch_a4(const double2* nlm, long long N, long long ld, double* out, long long ldo, cudaStream_t st);
 cudaError_t sfb_launch_eig(const double2* nlm, const double* M, long long N, long long ld, int plane, double* ei, double* lami,
@@ -862,6 +863,14 @@ int sfb_apply_bounds_arr(const double* nlm_in, double* nlm_out, int64_t N, int64
         for (int j = 15; j < g.n; ++j) memcpy(nlm_out + 2 * (size_t)j * ld, nlm_in + 2 * (size_t)j * ld, (size_t)N * 16);
     }
     CK(cudaMemcpy2D(nlm_out, (size_t)ld * 16, in.p, (size_t)N * 16, (size_t)N * 16, 15, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_apply_bounds_rnlm_arr_dev(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld_in, int64_t ld_out, void* stream) {
+    int rc = basic_check(rnlm_in, N, ld_in);
+    if (rc) return rc;
+    if (ld_out < N || (N && !rnlm_out)) return fail(SFB_EINVAL, "bad output");
+    CK(sfb_launch_bounds_rnlm(reinterpret_cast<const double2*>(rnlm_in), reinterpret_cast<double2*>(rnlm_out), N, ld_in, ld_out,
+                              sfb_rnlm_len(), (cudaStream_t)stream));
     return SFB_OK;
 }
 int sfb_nlm_to_rnlm_arr_dev(const double* nlm, double* rnlm, int64_t N, int64_t ld_nlm, int64_t ld_rnlm, void* stream) {

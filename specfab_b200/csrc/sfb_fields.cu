@@ -143,6 +143,33 @@ __global__ void __launch_bounds__(kBlock) bounds_kernel(const double2* __restric
         for (int j = 15; j < n; ++j) out[(long long)j * ldo + p] = in[(long long)j * ldi + p];
 }
 
+// apply_bounds on reduced-form states (what src/specfabpy/fenics/CPO.py:339-365 does per node through rnlm_to_nlm /
+// apply_bounds / nlm_to_rnlm): rows 0 | 1..3 (l = 2, m = 0..2) | 4..8 (l = 4, m = 0..4).  The power sums run over m = -l..l in
+// the full-form order with |n_l^-m|^2 = |n_l^m|^2, so the factors equal the full-form kernel's bit for bit.
+__global__ void __launch_bounds__(kBlock) bounds_rnlm_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long N,
+                                                             long long ldi, long long ldo, int r) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double2 v[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] = in[(long long)j * ldi + p];
+    const double S0 = v[0].x * v[0].x;
+    double s2 = 0.0, s4 = 0.0;       // same expression shape as bounds_kernel (the compiler contracts both the same way)
+#pragma unroll
+    for (int m = -2; m <= 2; ++m) { const double2 w = v[1 + (m < 0 ? -m : m)]; s2 += w.x * w.x + w.y * w.y; }
+#pragma unroll
+    for (int m = -4; m <= 4; ++m) { const double2 w = v[4 + (m < 0 ? -m : m)]; s4 += w.x * w.x + w.y * w.y; }
+    const double S2_rel = (1.0 / 5 * s2) / S0, S4_rel = (1.0 / 9 * s4) / S0;
+    const double f2 = S2_rel > 1.0 ? sqrt(S2_rel) : 1.0, f4 = S4_rel > 1.0 ? sqrt(S4_rel) : 1.0;
+    out[p] = v[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) out[(long long)j * ldo + p] = S2_rel > 1.0 ? make_double2(v[j].x / f2, v[j].y / f2) : v[j];
+#pragma unroll
+    for (int j = 4; j < 9; ++j) out[(long long)j * ldo + p] = S4_rel > 1.0 ? make_double2(v[j].x / f4, v[j].y / f4) : v[j];
+    if (in != out)
+        for (int j = 9; j < r; ++j) out[(long long)j * ldo + p] = in[(long long)j * ldi + p];
+}
+
 // nlm <-> rnlm (src/reducedform.f90:160-187).  rnlm rows are the m >= 0 coefficients in (l, m=0..l) order;
 // rnlm_to_nlm fills n_l^{-m} = (-1)^m conj(n_l^m).  blockIdx.y = full-form row j.
 __global__ void __launch_bounds__(kBlock) reduced_kernel(int to_reduced, const double2* __restrict__ src, double2* __restrict__ dst,
@@ -197,6 +224,10 @@ cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const 
 
 cudaError_t sfb_launch_bounds(const double2* in, double2* out, long long N, long long ldi, long long ldo, int n, cudaStream_t st) {
     if (N > 0) bounds_kernel<<<nblk(N), kBlock, 0, st>>>(in, out, N, ldi, ldo, n);
+    return cudaGetLastError();
+}
+cudaError_t sfb_launch_bounds_rnlm(const double2* in, double2* out, long long N, long long ldi, long long ldo, int r, cudaStream_t st) {
+    if (N > 0) bounds_rnlm_kernel<<<nblk(N), kBlock, 0, st>>>(in, out, N, ldi, ldo, r);
     return cudaGetLastError();
 }
 cudaError_t sfb_launch_reduced(int to_reduced, const double2* src, double2* dst, long long N, long long lds, long long ldd, int L,

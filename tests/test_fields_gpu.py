@@ -211,6 +211,13 @@ def test_apply_bounds_and_reduced_form():
     back = sf.rnlm_to_nlm_arr(r)
     assert np.abs(back - x).max() < 1e-16
     assert np.array_equal(sf.rnlm_to_nlm(sf.nlm_to_rnlm(x[1])), back[1])
+    # apply_bounds on the reduced-form field (what the FE coupler does per node): same factors as the full form, bit for bit
+    import torch
+    d = torch.from_numpy(np.ascontiguousarray(r.T)).cuda()
+    o = sf.apply_bounds_rnlm_arr_dev(d, out=torch.empty_like(d))
+    assert np.array_equal(o.cpu().numpy().T, sf.nlm_to_rnlm_arr(got))
+    sf.apply_bounds_rnlm_arr_dev(d)                          # in place
+    assert np.array_equal(d.cpu().numpy().T, sf.nlm_to_rnlm_arr(got))
 
 
 # ---------------------------------------------------------------------------------------------
