@@ -44,10 +44,24 @@ struct SfbRz {
     int ii, jj, s, zp, zn;
 };
 
+// the same, flattened for the export kernel: staged per CTA into shared memory with coalesced copies and read back as
+// broadcasts (the warp-uniform GLOBAL table loads were what the kernel waited on)
+struct SfbRzF {
+    int o;                 // ii + r * jj
+    int s;                 // sign of the (l, -m_jj) contribution: 0 (m_jj = 0), +1, -1
+    int ntp, ntn;          // number of terms of M(I(ii), +m_jj) and M(I(ii), -m_jj); both 0 = structural zero
+    int diag;              // ii == jj: M_DDRX subtracts <D> here
+    int fp[3], fn[3];
+    int pad;
+    double cp[3], cn[3];
+};
+static_assert(sizeof(SfbRzF) == 96, "flat record: 6 x 16 bytes");
+
 struct DevLists {
     int L = 0;
     SfbNz *lrot = nullptr, *ddrx = nullptr;
     SfbRz *rlrot = nullptr, *rddrx = nullptr;
+    SfbRzF *flrot = nullptr, *fddrx = nullptr;
     int n_lrot = 0, n_ddrx = 0, n_rlrot = 0, n_rddrx = 0;
 } g_lists[64];
 
@@ -63,8 +77,10 @@ void reduced_list(int L, const std::vector<SfbNz>& nz, std::vector<SfbRz>& out) 
             for (int lj = 0; lj <= L; lj += 2)
                 for (int mj = 0; mj <= lj; ++mj, ++jj) {
                     const int jp = lj * (lj + 1) / 2 + mj, jn = jp - 2 * mj;
+                    // every (ii, jj) is listed, structural zeros too (zp = zn = -1): the export kernel writes each output entry
+                    // exactly once and needs no memset pass over the 4 r^2 8-byte planes per node
                     SfbRz r{ii, jj, mj == 0 ? 0 : ((mj & 1) ? -1 : 1), where[(size_t)ip * n + jp], where[(size_t)ip * n + jn]};
-                    if (r.zp >= 0 || r.zn >= 0) out.push_back(r);
+                    out.push_back(r);
                 }
         }
 }
@@ -220,27 +236,51 @@ __global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNz
 }
 
 // the same operators written directly in reduced form (Mrr, Mri, Mir, Mii each (N, r, r) real), src/reducedform.f90:76-120
-__global__ void __launch_bounds__(kThreads) mexport_reduced_kernel(int mode, const SfbNz* __restrict__ nz, const SfbRz* __restrict__ rz,
-                                                                   int nrz, int r, const double* __restrict__ a33,
+constexpr int kRzBatch = 96;      // flat records staged per pass (9 KB of shared memory)
+__global__ void __launch_bounds__(kThreads) mexport_reduced_kernel(int mode, const SfbRzF* __restrict__ rf, int nrz, int r,
+                                                                   const double* __restrict__ a33,
                                                                    const double* __restrict__ b33, const double2* __restrict__ nlm,
                                                                    long long ldn, long long N, long long ld, double iota, double zeta,
                                                                    double* __restrict__ Mrr, double* __restrict__ Mri,
                                                                    double* __restrict__ Mir, double* __restrict__ Mii, long long ldm) {
-    __shared__ double2 f[kNF][kTN];
+    // forcing entries 0..7 (M_LROT) or 8..22 (M_DDRX*): at most 15 of the kNF rows are live in one launch
+    __shared__ double2 fbuf[15][kTN];
+    __shared__ __align__(16) SfbRzF recs[kRzBatch];
+    double2 (*f)[kTN] = fbuf - (mode == 0 ? 0 : 8);
     const int t = threadIdx.x;
     const long long p = (long long)blockIdx.x * kTN + t;
-    if (p >= N) return;
-    const double davg = mexport_forcing(mode, f, t, p, a33, b33, nlm, ldn, ld, iota, zeta);
-    for (int z = blockIdx.y; z < nrz; z += gridDim.y) {
-        const SfbRz e = rz[z];
-        const double2 vp = e.zp >= 0 ? nz_value(nz[e.zp], f, t, mode, davg) : make_double2(0.0, 0.0);
-        const double2 vn = e.zn >= 0 ? nz_value(nz[e.zn], f, t, mode, davg) : make_double2(0.0, 0.0);
-        const long long o = ((long long)e.ii + (long long)r * e.jj) * ldm + p;
-        const double s = (double)e.s;
-        Mrr[o] = vp.x + s * vn.x;
-        Mri[o] = -vp.y + s * vn.y;
-        Mir[o] = vp.y + s * vn.y;
-        Mii[o] = vp.x - s * vn.x;
+    const bool valid = p < N;
+    const double davg = valid ? mexport_forcing(mode, f, t, p, a33, b33, nlm, ldn, ld, iota, zeta) : 0.0;
+    // the forcing preparation above is repeated by every blockIdx.y: each CTA takes a contiguous share of the r^2 entries of
+    // the dense list and writes every one of them exactly once, structural zeros included (no memset pass over the output)
+    const int per = (nrz + gridDim.y - 1) / gridDim.y, z0 = blockIdx.y * per, z1 = min(nrz, z0 + per);
+    for (int zb = z0; zb < z1; zb += kRzBatch) {
+        const int nb = min(kRzBatch, z1 - zb);
+        __syncthreads();
+        {   // coalesced 16-byte copies of nb records
+            const int4* src = reinterpret_cast<const int4*>(rf + zb);
+            int4* dst = reinterpret_cast<int4*>(recs);
+            for (int q = t; q < nb * 6; q += kThreads) dst[q] = src[q];
+        }
+        __syncthreads();
+        if (!valid) continue;
+        for (int z = 0; z < nb; ++z) {
+            const SfbRzF& e = recs[z];
+            const long long o = (long long)e.o * ldm + p;
+            if ((e.ntp | e.ntn) == 0) {
+                __stcs(Mrr + o, 0.0); __stcs(Mri + o, 0.0); __stcs(Mir + o, 0.0); __stcs(Mii + o, 0.0);
+                continue;
+            }
+            double2 vp = make_double2(0.0, 0.0), vn = make_double2(0.0, 0.0);
+            for (int q = 0; q < e.ntp; ++q) { const double2 ff = f[e.fp[q]][t]; vp.x = fma(e.cp[q], ff.x, vp.x); vp.y = fma(e.cp[q], ff.y, vp.y); }
+            for (int q = 0; q < e.ntn; ++q) { const double2 ff = f[e.fn[q]][t]; vn.x = fma(e.cn[q], ff.x, vn.x); vn.y = fma(e.cn[q], ff.y, vn.y); }
+            if (mode == 2 && e.diag) vp.x -= davg;
+            const double s = (double)e.s;
+            __stcs(Mrr + o, vp.x + s * vn.x);
+            __stcs(Mri + o, -vp.y + s * vn.y);
+            __stcs(Mir + o, vp.y + s * vn.y);
+            __stcs(Mii + o, vp.x - s * vn.x);
+        }
     }
 }
 
@@ -301,9 +341,26 @@ cudaError_t sfb_ops_prepare(int L) {
     std::vector<SfbRz> ra, rb;
     reduced_list(L, a, ra);
     reduced_list(L, b, rb);
-    cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx);
+    const int r = (L + 2) * (L + 2) / 4;
+    auto flatten = [&](const std::vector<SfbNz>& nz, const std::vector<SfbRz>& rz) {
+        std::vector<SfbRzF> out(rz.size());
+        for (size_t z = 0; z < rz.size(); ++z) {
+            SfbRzF f{};
+            f.o = rz[z].ii + r * rz[z].jj; f.s = rz[z].s; f.diag = rz[z].ii == rz[z].jj;
+            if (rz[z].zp >= 0) { const SfbNz& e = nz[rz[z].zp]; f.ntp = e.nt; for (int q = 0; q < e.nt; ++q) { f.fp[q] = e.fidx[q]; f.cp[q] = e.c[q]; } }
+            if (rz[z].zn >= 0 && rz[z].s != 0) { const SfbNz& e = nz[rz[z].zn]; f.ntn = e.nt; for (int q = 0; q < e.nt; ++q) { f.fn[q] = e.fidx[q]; f.cn[q] = e.c[q]; } }
+            out[z] = f;
+        }
+        return out;
+    };
+    const std::vector<SfbRzF> fa = flatten(a, ra), fb = flatten(b, rb);
+    cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); cudaFree(d.flrot); cudaFree(d.fddrx);
     d = DevLists();
     cudaError_t e;
+    if ((e = cudaMalloc(&d.flrot, fa.size() * sizeof(SfbRzF))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d.fddrx, fb.size() * sizeof(SfbRzF))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.flrot, fa.data(), fa.size() * sizeof(SfbRzF), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.fddrx, fb.data(), fb.size() * sizeof(SfbRzF), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d.rlrot, ra.size() * sizeof(SfbRz))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d.rddrx, rb.size() * sizeof(SfbRz))) != cudaSuccess) return e;
     if ((e = cudaMemcpy(d.rlrot, ra.data(), ra.size() * sizeof(SfbRz), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -318,7 +375,7 @@ cudaError_t sfb_ops_prepare(int L) {
 }
 
 void sfb_ops_release() {
-    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); d = DevLists(); }
+    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); cudaFree(d.flrot); cudaFree(d.fddrx); d = DevLists(); }
 }
 
 // M must be zero-filled by the caller side of the launcher (done here with cudaMemsetAsync)
@@ -348,15 +405,17 @@ cudaError_t sfb_launch_mexport_reduced(int mode, int L, const double* a33, const
     cudaGetDevice(&dev);
     const DevLists& d = g_lists[dev & 63];
     const int r = (L + 2) * (L + 2) / 4;
-    double* outs[4] = {Mrr, Mri, Mir, Mii};
-    for (double* o : outs)
-        if ((e = cudaMemsetAsync(o, 0, (size_t)N * r * r * sizeof(double), st)) != cudaSuccess) return e;
     if (N <= 0) return cudaSuccess;
-    const SfbNz* nz = mode == 0 ? d.lrot : d.ddrx;
-    const SfbRz* rz = mode == 0 ? d.rlrot : d.rddrx;
+    const SfbRzF* rf = mode == 0 ? d.flrot : d.fddrx;
     const int nrz = mode == 0 ? d.n_rlrot : d.n_rddrx;
-    dim3 grid((unsigned)((N + kTN - 1) / kTN), (unsigned)std::min(nrz, 64));
-    mexport_reduced_kernel<<<grid, kThreads, 0, st>>>(mode, nz, rz, nrz, r, a33, b33, nlm, ldn, N, ld, iota, zeta, Mrr, Mri, Mir, Mii, N);
+    // nrz = r^2 (dense list).  Entries per CTA: enough to amortise the per-node forcing preparation (M_DDRX: weights and <D>),
+    // few enough to keep >= ~4 CTAs per SM in flight on small batches
+    const int kRzPerCta = 96;
+    const long long xt = (N + kTN - 1) / kTN;
+    int gy = std::max(1, std::min((nrz + kRzPerCta - 1) / kRzPerCta, 64));
+    while (gy < 64 && gy < nrz && xt * gy < 4 * 148) ++gy;
+    dim3 grid((unsigned)xt, (unsigned)gy);
+    mexport_reduced_kernel<<<grid, kThreads, 0, st>>>(mode, rf, nrz, r, a33, b33, nlm, ldn, N, ld, iota, zeta, Mrr, Mri, Mir, Mii, N);
     return cudaGetLastError();
 }
 
