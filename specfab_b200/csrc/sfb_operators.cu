@@ -56,12 +56,21 @@ struct SfbRzF {
     double cp[3], cn[3];
 };
 static_assert(sizeof(SfbRzF) == 96, "flat record: 6 x 16 bytes");
+// dense (N, n, n) export: one record per output entry M(i, j), structural zeros included (nt = 0)
+struct SfbNzF {
+    int o;                 // i + n * j
+    int nt, diag, pad;
+    int fidx[3], pad2;
+    double c[3], pad3;
+};
+static_assert(sizeof(SfbNzF) == 64, "flat record: 4 x 16 bytes");
 
 struct DevLists {
     int L = 0;
     SfbNz *lrot = nullptr, *ddrx = nullptr;
     SfbRz *rlrot = nullptr, *rddrx = nullptr;
     SfbRzF *flrot = nullptr, *fddrx = nullptr;
+    SfbNzF *dlrot = nullptr, *dddrx = nullptr;        // n^2 records each
     int n_lrot = 0, n_ddrx = 0, n_rlrot = 0, n_rddrx = 0;
 } g_lists[64];
 
@@ -220,18 +229,38 @@ __device__ __forceinline__ double2 nz_value(const SfbNz& e, const double2 (*f)[k
     return v;
 }
 
-__global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNz* __restrict__ nz, int nnz, int n,
+constexpr int kNzBatch = 160;     // flat records staged per pass (10 KB of shared memory)
+__global__ void __launch_bounds__(kThreads) mexport_kernel(int mode, const SfbNzF* __restrict__ nf, int nent,
                                                            const double* __restrict__ a33, const double* __restrict__ b33,
                                                            const double2* __restrict__ nlm, long long ldn, long long N, long long ld,
                                                            double iota, double zeta, double2* __restrict__ M, long long ldm) {
-    __shared__ double2 f[kNF][kTN];
+    // same scheme as mexport_reduced_kernel below: every one of the n^2 entries is written exactly once (no memset pass), the
+    // CTA's contiguous share of the table is staged through shared memory, the forcing preparation is amortised over it
+    __shared__ double2 fbuf[15][kTN];
+    __shared__ __align__(16) SfbNzF recs[kNzBatch];
+    double2 (*f)[kTN] = fbuf - (mode == 0 ? 0 : 8);
     const int t = threadIdx.x;
     const long long p = (long long)blockIdx.x * kTN + t;
-    if (p >= N) return;
-    const double davg = mexport_forcing(mode, f, t, p, a33, b33, nlm, ldn, ld, iota, zeta);
-    for (int z = blockIdx.y; z < nnz; z += gridDim.y) {
-        const SfbNz e = nz[z];
-        M[((long long)e.i + (long long)n * e.j) * ldm + p] = nz_value(e, f, t, mode, davg);
+    const bool valid = p < N;
+    const double davg = valid ? mexport_forcing(mode, f, t, p, a33, b33, nlm, ldn, ld, iota, zeta) : 0.0;
+    const int per = (nent + gridDim.y - 1) / gridDim.y, z0 = blockIdx.y * per, z1 = min(nent, z0 + per);
+    for (int zb = z0; zb < z1; zb += kNzBatch) {
+        const int nb = min(kNzBatch, z1 - zb);
+        __syncthreads();
+        {
+            const int4* src = reinterpret_cast<const int4*>(nf + zb);
+            int4* dst = reinterpret_cast<int4*>(recs);
+            for (int q = t; q < nb * 4; q += kThreads) dst[q] = src[q];
+        }
+        __syncthreads();
+        if (!valid) continue;
+        for (int z = 0; z < nb; ++z) {
+            const SfbNzF& e = recs[z];
+            double2 v = make_double2(0.0, 0.0);
+            for (int q = 0; q < e.nt; ++q) { const double2 ff = f[e.fidx[q]][t]; v.x = fma(e.c[q], ff.x, v.x); v.y = fma(e.c[q], ff.y, v.y); }
+            if (mode == 2 && e.diag && e.nt) v.x -= davg;
+            __stcs(M + (long long)e.o * ldm + p, v);
+        }
     }
 }
 
@@ -354,9 +383,26 @@ cudaError_t sfb_ops_prepare(int L) {
         return out;
     };
     const std::vector<SfbRzF> fa = flatten(a, ra), fb = flatten(b, rb);
-    cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); cudaFree(d.flrot); cudaFree(d.fddrx);
+    const int nn = (L + 1) * (L + 2) / 2;
+    auto densify = [&](const std::vector<SfbNz>& nz) {
+        std::vector<SfbNzF> out((size_t)nn * nn);
+        for (int j = 0; j < nn; ++j)
+            for (int i = 0; i < nn; ++i) { SfbNzF f{}; f.o = i + nn * j; f.diag = i == j; out[(size_t)i + (size_t)nn * j] = f; }
+        for (const SfbNz& e : nz) {
+            SfbNzF& f = out[(size_t)e.i + (size_t)nn * e.j];
+            f.nt = e.nt;
+            for (int q = 0; q < e.nt; ++q) { f.fidx[q] = e.fidx[q]; f.c[q] = e.c[q]; }
+        }
+        return out;
+    };
+    const std::vector<SfbNzF> da = densify(a), db = densify(b);
+    cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); cudaFree(d.flrot); cudaFree(d.fddrx); cudaFree(d.dlrot); cudaFree(d.dddrx);
     d = DevLists();
     cudaError_t e;
+    if ((e = cudaMalloc(&d.dlrot, da.size() * sizeof(SfbNzF))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&d.dddrx, db.size() * sizeof(SfbNzF))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.dlrot, da.data(), da.size() * sizeof(SfbNzF), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d.dddrx, db.data(), db.size() * sizeof(SfbNzF), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d.flrot, fa.size() * sizeof(SfbRzF))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&d.fddrx, fb.size() * sizeof(SfbRzF))) != cudaSuccess) return e;
     if ((e = cudaMemcpy(d.flrot, fa.data(), fa.size() * sizeof(SfbRzF), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -375,7 +421,7 @@ cudaError_t sfb_ops_prepare(int L) {
 }
 
 void sfb_ops_release() {
-    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); cudaFree(d.flrot); cudaFree(d.fddrx); d = DevLists(); }
+    for (auto& d : g_lists) { cudaFree(d.lrot); cudaFree(d.ddrx); cudaFree(d.rlrot); cudaFree(d.rddrx); cudaFree(d.flrot); cudaFree(d.fddrx); cudaFree(d.dlrot); cudaFree(d.dddrx); d = DevLists(); }
 }
 
 // M must be zero-filled by the caller side of the launcher (done here with cudaMemsetAsync)
@@ -387,12 +433,14 @@ cudaError_t sfb_launch_mexport(int mode, int L, const double* a33, const double*
     cudaGetDevice(&dev);
     const DevLists& d = g_lists[dev & 63];
     const int n = (L + 1) * (L + 2) / 2;
-    if ((e = cudaMemsetAsync(M, 0, (size_t)N * n * n * sizeof(double2), st)) != cudaSuccess) return e;
     if (N <= 0) return cudaSuccess;
-    const SfbNz* nz = mode == 0 ? d.lrot : d.ddrx;
-    const int nnz = mode == 0 ? d.n_lrot : d.n_ddrx;
-    dim3 grid((unsigned)((N + kTN - 1) / kTN), (unsigned)std::min(nnz, 64));
-    mexport_kernel<<<grid, kThreads, 0, st>>>(mode, nz, nnz, n, a33, b33, nlm, ldn, N, ld, iota, zeta, M, N);
+    const SfbNzF* nf = mode == 0 ? d.dlrot : d.dddrx;
+    const int nent = n * n;
+    const long long xt = (N + kTN - 1) / kTN;
+    int gy = std::max(1, std::min((nent + 191) / 192, 64));
+    while (gy < 64 && xt * gy < 4 * 148) ++gy;
+    dim3 grid((unsigned)xt, (unsigned)gy);
+    mexport_kernel<<<grid, kThreads, 0, st>>>(mode, nf, nent, a33, b33, nlm, ldn, N, ld, iota, zeta, M, N);
     return cudaGetLastError();
 }
 

@@ -31,7 +31,16 @@ for L, N in ((8, 100_000), (12, 40_000), (4, 400_000)):
     def ddrx():
         _lib.check(lib.sfb_M_DDRX_reduced_arr_dev(x.data_ptr(), N, Td.data_ptr(), N, N, 0, *ptrs, None))
 
-    for name, fn in (("M_LROT_reduced", lrot), ("M_DDRX_reduced", ddrx)):
+    Nd = max(N // 4, 1000)                                      # dense (N, n, n) complex(8) output: 16 n^2 B per node
+    Md = torch.empty((n, n, Nd), dtype=torch.complex128, device="cuda")
+
+    def lrot_dense():
+        _lib.check(lib.sfb_M_LROT_arr_dev(Dd.data_ptr(), Wd.data_ptr(), Nd, N, 1.0, 0.0, Md.data_ptr(), None))
+
+    def ddrx_dense():
+        _lib.check(lib.sfb_M_DDRX_arr_dev(x.data_ptr(), N, Td.data_ptr(), Nd, N, Md.data_ptr(), None))
+
+    for name, fn in (("M_LROT_reduced", lrot), ("M_DDRX_reduced", ddrx), ("M_LROT_dense", lrot_dense), ("M_DDRX_dense", ddrx_dense)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -41,5 +50,7 @@ for L, N in ((8, 100_000), (12, 40_000), (4, 400_000)):
             fn()
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 10
-        gbs = 4 * r * r * 8 * N / (ms * 1e-3) / 1e9
-        print(json.dumps(dict(op=name, L=L, N=N, ms=round(ms, 4), nodes_per_s=round(N / (ms * 1e-3)), out_gbs=round(gbs, 1), hbm_frac=round(gbs / HBM, 3))), flush=True)
+        dense = name.endswith("dense")
+        Nn = Nd if dense else N
+        gbs = (16 * n * n if dense else 4 * r * r * 8) * Nn / (ms * 1e-3) / 1e9
+        print(json.dumps(dict(op=name, L=L, N=Nn, ms=round(ms, 4), nodes_per_s=round(Nn / (ms * 1e-3)), out_gbs=round(gbs, 1), hbm_frac=round(gbs / HBM, 3))), flush=True)
