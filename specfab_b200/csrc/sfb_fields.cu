@@ -171,23 +171,25 @@ __global__ void __launch_bounds__(kBlock) bounds_rnlm_kernel(const double2* __re
 }
 
 // nlm <-> rnlm (src/reducedform.f90:160-187).  rnlm rows are the m >= 0 coefficients in (l, m=0..l) order;
-// rnlm_to_nlm fills n_l^{-m} = (-1)^m conj(n_l^m).  blockIdx.y = full-form row j.
+// rnlm_to_nlm fills n_l^{-m} = (-1)^m conj(n_l^m).  One thread per node walks the REDUCED rows of one degree group
+// (blockIdx.y = l/2): each source element is read once and written to its one (to_reduced) or two (mirror) destinations,
+// with all loads of the group in flight together.
 __global__ void __launch_bounds__(kBlock) reduced_kernel(int to_reduced, const double2* __restrict__ src, double2* __restrict__ dst,
                                                          long long N, long long lds, long long ldd, int L) {
     const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (p >= N) return;
-    const int j = blockIdx.y;                                // full-form row
-    int l = 0;
-    while ((l + 2) * (l + 3) / 2 - (l + 2) <= j) l += 2;
-    const int m = j - l * (l + 1) / 2;
-    const int am = m < 0 ? -m : m;
-    const int r = (l / 2) * (l / 2) + am;                    // reduced row of (l, |m|): sum_{l'<l}(l'+1) + |m| = (l/2)^2 + |m|
-    if (to_reduced) {
-        if (m >= 0) dst[(long long)r * ldd + p] = src[(long long)j * lds + p];
-    } else {
-        double2 v = src[(long long)r * lds + p];
-        if (m < 0) { v.y = -v.y; if (am & 1) { v.x = -v.x; v.y = -v.y; } }
-        dst[(long long)j * ldd + p] = v;
+    const int h = blockIdx.y, l = 2 * h;
+    const int rb = h * h, fb = l * (l + 1) / 2;              // reduced row of (l, 0), full-form row of (l, 0)
+    (void)L;
+#pragma unroll 4
+    for (int m = 0; m <= l; ++m) {
+        if (to_reduced) {
+            __stcs(dst + (long long)(rb + m) * ldd + p, __ldcs(src + (long long)(fb + m) * lds + p));
+        } else {
+            const double2 v = __ldcs(src + (long long)(rb + m) * lds + p);
+            __stcs(dst + (long long)(fb + m) * ldd + p, v);
+            if (m) __stcs(dst + (long long)(fb - m) * ldd + p, (m & 1) ? make_double2(-v.x, v.y) : make_double2(v.x, -v.y));
+        }
     }
 }
 
@@ -232,7 +234,6 @@ cudaError_t sfb_launch_bounds_rnlm(const double2* in, double2* out, long long N,
 }
 cudaError_t sfb_launch_reduced(int to_reduced, const double2* src, double2* dst, long long N, long long lds, long long ldd, int L,
                                cudaStream_t st) {
-    const int n = (L + 1) * (L + 2) / 2;
-    if (N > 0) reduced_kernel<<<dim3(nblk(N), n), kBlock, 0, st>>>(to_reduced, src, dst, N, lds, ldd, L);
+    if (N > 0) reduced_kernel<<<dim3(nblk(N), L / 2 + 1), kBlock, 0, st>>>(to_reduced, src, dst, N, lds, ldd, L);
     return cudaGetLastError();
 }
