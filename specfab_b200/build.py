@@ -74,7 +74,8 @@ EXP = {
     # short m blocks); without any test the kernel would run at 0.485 ms (profiles/r01_notes.md); global stores in a rolled
     # epilogue loop instead of the unrolled stage body ("+ep": body 8 % shorter, L = 8 RK4 0.558 -> 0.573 ms, L = 10 0.949 -> 0.893 ms);
     # mirror rows prefetched to L2 at the head of the tile and tested in the LAST stage next to the n0 re-reads, stores in an epilogue
-    # ("+lsym": 0.557 -> 0.663 ms)
+    # ("+lsym": 0.557 -> 0.663 ms); general tiles handed to a second launch through a work list ("+fb2": no in-kernel fallback
+    # call, no spills: RK4 0.556 -> 0.537 ms, but Euler 0.260 -> 0.296 ms and general states 0.35 -> 0.56 ms per 2e5 nodes)
 }
 # default variant (0), chosen from the sweeps in profiles/r01_variants_sweep*.txt.
 #   L <= 8 (code fits the instruction cache): straight-line kernels, small tiles, several independent CTAs per SM;
