@@ -42,6 +42,16 @@ cases = [
     ("reduce_M (complex)", Nm, 16 * n * n + 32 * r * r, lambda: lib.sfb_reduce_M_arr_dev(P(Mc), 1, Nm, Nm, *[P(t) for t in R4], None)),
     ("M_REG_arr", Nm, 8 * n * n + 72, lambda: lib.sfb_M_REG_arr_dev(P(eps), Nm, N, P(Mr), None)),
 ]
+a4in = f64(81, N)
+a6in = f64(729, Na6)
+a2in = f64(9, N)
+for t_ in (a2in, a4in, a6in):
+    t_.normal_()
+cases += [
+    ("a2_to_nlm", N, 72 + 6 * 16, lambda: lib.sfb_ai_to_nlm_arr_dev(2, P(a2in), N, N, P(xo), N, None)),
+    ("a4_to_nlm", N, 648 + 15 * 16, lambda: lib.sfb_ai_to_nlm_arr_dev(4, P(a4in), N, N, P(xo), N, None)),
+    ("a6_to_nlm", Na6, 5832 + 28 * 16, lambda: lib.sfb_ai_to_nlm_arr_dev(6, P(a6in), Na6, Na6, P(xo), N, None)),
+]
 for name, Nn, bytes_node, fn in cases:
     for _ in range(3):
         _lib.check(fn())
