@@ -32,6 +32,13 @@ module specfab_b200
             integer(c_int64_t), value :: N, ld
             type(sfb_step_opts), intent(in) :: opts
         end function
+        ! page-lock an existing array once (4x faster host-pointer calls), release before deallocation
+        integer(c_int) function sfb_host_register(p, bytes) bind(c, name='sfb_host_register')
+            import; type(c_ptr), value :: p; integer(c_int64_t), value :: bytes
+        end function
+        integer(c_int) function sfb_host_unregister(p) bind(c, name='sfb_host_unregister')
+            import; type(c_ptr), value :: p
+        end function
         ! the same step on reduced-form states rnlm(N, rnlm_len) (src/reducedform.f90:160-187)
         integer(c_int) function sfb_step_rnlm_arr(rnlm_in, rnlm_out, N, ld, ugrad, tau, opts) bind(c, name='sfb_step_rnlm_arr')
             import; type(c_ptr), value :: rnlm_in, rnlm_out, ugrad, tau

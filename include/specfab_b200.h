@@ -235,6 +235,11 @@ int sfb_memcpy_h2d(void* dst, const void* src, int64_t bytes);
 int sfb_memcpy_d2h(void* dst, const void* src, int64_t bytes);
 int sfb_host_alloc_pinned(void** p, int64_t bytes);
 int sfb_host_free_pinned(void* p);
+/* Page-lock an EXISTING host array (a Fortran allocatable, a numpy array) so that the host-pointer entry points move it by
+ * DMA at PCIe speed: sfb_step_arr on pageable memory is staged by the driver and ~4x slower (1.3e7 vs 5.6e7 node-updates/s,
+ * BASELINE config 2 on B200).  Register once, reuse every step, unregister before the array is freed. */
+int sfb_host_register(void* p, int64_t bytes);
+int sfb_host_unregister(void* p);
 int sfb_sync(void);
 int sfb_device_count(void);
 int sfb_set_device(int dev);

@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import (SFB_LROT, SFB_DDRX, SFB_CDRX, SFB_REG, SFB_EULER, SFB_RK4, SpecfabB200Error, StepOpts)
 
 __all__ = ["apply_bounds", "apply_bounds_arr", "nlm_to_rnlm", "rnlm_to_nlm", "nlm_to_rnlm_arr", "rnlm_to_nlm_arr", "rnlm_len", "M_LROT", "M_DDRX", "M_DDRX_src", "M_CDRX", "M_REG", "dndt_LATROT", "dndt_DDRX", "dndt_CDRX", "dndt_REG", "reduce_M", "reduce_M_arr", "M_LROT_reduced_arr", "M_DDRX_reduced_arr", "M_LROT_arr", "M_DDRX_arr", "M_DDRX_src_arr", "M_REG_arr",
-           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "step_moments_Eij_rnlm_arr_dev", "apply_bounds_rnlm_arr_dev", "build_info", "layout_nlm", "layout_mat",
+           "nlm_LROT", "init", "nlm_len", "step_arr", "step_arr_dev", "step_rnlm_arr", "step_rnlm_arr_dev", "step_moments_Eij_rnlm_arr_dev", "apply_bounds_rnlm_arr_dev", "pin_array", "unpin_array", "build_info", "layout_nlm", "layout_mat",
            "a2", "a4", "eig", "a2_arr", "a4_arr", "eig_arr", "eigframe_arr", "Eij_tranisotropic", "Eij_tranisotropic_arr",
            "a6", "a6_arr", "a2_to_nlm", "a4_to_nlm", "a6_to_nlm", "a2_to_nlm_arr", "a4_to_nlm_arr", "a6_to_nlm_arr", "E_CAFFE", "E_CAFFE_arr", "pfJ", "pfJ_arr", "Eij_eigenframe_arr", "Eij_orthotropic", "Eij_orthotropic_arr", "Eij_orthotropic_arr_dev", "a2_arr_dev", "Eij_eigenframe_arr_dev", "step_moments_Eij_arr_dev", "Eij_tranisotropic_arr_dev",
            "SFB_LROT", "SFB_DDRX", "SFB_CDRX", "SFB_REG", "SFB_EULER", "SFB_RK4", "SpecfabB200Error"]
@@ -296,6 +296,22 @@ def apply_bounds_arr(nlm):
     out = np.empty((N, n), dtype=np.complex128, order="F")
     _lib.check(_lib.load().sfb_apply_bounds_arr(x.ctypes.data, out.ctypes.data, N, N))
     return out
+
+
+def pin_array(a):
+    """Page-lock an existing numpy array in place (cudaHostRegister) so that the host-array entry points (step_arr, ...)
+    move it by DMA at PCIe speed; pageable arrays are ~4x slower.  Keep the array alive and call unpin_array(a) before it
+    is freed.  Returns a."""
+    if not isinstance(a, np.ndarray) or a.nbytes == 0:
+        raise ValueError("pin_array needs a non-empty numpy array")
+    if not (a.flags.c_contiguous or a.flags.f_contiguous):
+        raise ValueError("pin_array needs a contiguous array")
+    _lib.check(_lib.load().sfb_host_register(a.ctypes.data, a.nbytes))
+    return a
+
+
+def unpin_array(a):
+    _lib.check(_lib.load().sfb_host_unregister(a.ctypes.data))
 
 
 def apply_bounds_rnlm_arr_dev(rnlm, out=None):

@@ -99,6 +99,8 @@ SIGNATURES = {
     "sfb_memcpy_d2h": (C.c_int, [_P, _P, _I64]),
     "sfb_host_alloc_pinned": (C.c_int, [C.POINTER(_P), _I64]),
     "sfb_host_free_pinned": (C.c_int, [_P]),
+    "sfb_host_register": (C.c_int, [_P, _I64]),
+    "sfb_host_unregister": (C.c_int, [_P]),
     "sfb_sync": (C.c_int, []),
     "sfb_device_count": (C.c_int, []),
     "sfb_set_device": (C.c_int, [C.c_int]),

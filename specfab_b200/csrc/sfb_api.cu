@@ -918,6 +918,16 @@ int sfb_host_alloc_pinned(void** p, int64_t bytes) {
     return SFB_OK;
 }
 int sfb_host_free_pinned(void* p) { CK(cudaFreeHost(p)); return SFB_OK; }
+int sfb_host_register(void* p, int64_t bytes) {
+    if (!p || bytes <= 0) return fail(SFB_EINVAL, "sfb_host_register: null pointer or empty range");
+    CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+    return SFB_OK;
+}
+int sfb_host_unregister(void* p) {
+    if (!p) return fail(SFB_EINVAL, "sfb_host_unregister: null pointer");
+    CK(cudaHostUnregister(p));
+    return SFB_OK;
+}
 int sfb_sync(void) { CK(cudaDeviceSynchronize()); return SFB_OK; }
 int sfb_device_count(void) {
     int n = 0;

@@ -340,3 +340,24 @@ def test_reduced_form_step_errors_and_empty():
             sf.step_rnlm_arr(sf.nlm_to_rnlm_arr(random_states(L, 4, 1, True)), random_ugrad(4, 2), dt=1e-3)
     finally:
         _lib.load().sfb_set_variant(0)
+
+
+def test_pin_array_in_place():
+    """page-locking the caller's own arrays (sfb_host_register) changes the speed of the host-pointer path, not its result"""
+    import specfab_b200 as sf
+    L, N = 8, 5000
+    lm, n = sf.init(L)
+    x = np.asfortranarray(random_states(L, N, 41, True))
+    ug = np.asfortranarray(random_ugrad(N, 42))
+    ref = sf.step_arr(x, ug, dt=1e-3, scheme="rk4")
+    out = np.empty((N, n), dtype=np.complex128, order="F")
+    for a in (x, ug, out):
+        sf.pin_array(a)
+    try:
+        got = sf.step_arr(x, ug, dt=1e-3, scheme="rk4", out=out)
+        assert got is out and np.array_equal(out, ref)
+    finally:
+        for a in (x, ug, out):
+            sf.unpin_array(a)
+    with pytest.raises(ValueError):
+        sf.pin_array(np.zeros((4, 4))[::2])
