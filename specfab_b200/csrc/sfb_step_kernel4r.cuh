@@ -174,6 +174,20 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
         }
     }
     const double* dbuf = reinterpret_cast<const double*>(bufs) + 2 * nl + comp;      // this lane's component column
+#if SFB_DDRX
+    // <D> of the first stage needs only the staged state and tau: computed here, in front of the barrier the symmetry verdict
+    // needs anyway (the rate factor scal[SC_G0] is another thread's: it is applied after that barrier), so stage 0 has no
+    // barrier of its own
+    if (tid < nvalid) {
+        const double2* y = bufs + tid;
+        double2 n2[3], n4[5];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) n2[m] = y[pslot(2, m) * kTNR];
+#pragma unroll
+        for (int m = 0; m < 5; ++m) n4[m] = (kL >= 4) ? y[pslot(4, m) * kTNR] : make_double2(0.0, 0.0);
+        scal[SC_C0 * kTNR + tid] = ddrx_davg(global_src(P, node0 + tid), y[0], n2, n4);
+    }
+#endif
 
     // ---- real-ODF symmetry of the input to round-off, each lane tests its own component of the mirror rows
     bool bad = false;
@@ -244,6 +258,9 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
         }
 #endif
 #if SFB_DDRX
+        if (s == 0) {         // computed in front of the symmetry barrier
+            c.c0 = -(scal[SC_G0 * kTNR + nl] * scal[SC_C0 * kTNR + nl]);
+        } else {
         if (tid < nvalid) {   // <D>(current stage state), one thread per node
             const double2* y = bufs + (size_t)ib * kNRowR * kTNR + tid;
             double2 n2[3], n4[5];
@@ -256,6 +273,7 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
         }
         __syncthreads();
         c.c0 = scal[SC_C0 * kTNR + nl];
+        }
 #endif
         apply_reduced<RIO>(c);
         if (!c.last) __syncthreads();
