@@ -64,6 +64,10 @@ EXTRA = {
 }
 # variants under test (SFB_EXP_VARIANTS=1)
 EXP = {
+    # windowed loop kernel: (variant, -6, one-warp tiles per CTA, register cap)
+    (8, 1): [(60, -6, 1, 168, "", False), (61, -6, 1, 255, "", False), (62, -6, 1, 200, "", False), (63, -6, 1, 232, "", False), (64, -6, 4, 255, "", False),
+             (65, -6, 1, 184, "", False), (66, -6, 4, 168, "", False)],
+    (8, 0): [(60, -6, 1, 168, "", False), (61, -6, 1, 128, "", False), (62, -6, 4, 168, "", False)],
     # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
@@ -157,6 +161,24 @@ def generate(Ls):
                 window = "w" in parts[1:]
                 mc = max([int(x[1:]) for x in parts[1:] if x.startswith("c") and not x.startswith(("ch", "cw"))] + [1])
                 gd = max([int(x[1:]) for x in parts[1:] if x.startswith("g")] + [0])
+                if R == -6:      # windowed loop kernel (one lane per node, register window, constant-cache table); TN field = one-warp tiles per CTA, MINB field = register cap
+                    from specfab_b200.codegen import emit_wloop
+                    wtab, wmeta = emit_wloop.emit(L, dd)
+                    _write_if_changed(os.path.join(GEN, "wtab_L%d_%s.inc" % (L, "ddrx" if dd else "lrot")), wtab)
+                    meta = dict(L=L, ddrx=dd, R=1, TN=32, reduced=1, wloop=1, WPC=TN,
+                                dfma_node=sum(p.dfma for p in emit_step.plan(L, dd)[1]),
+                                dfma_executed=wmeta["dfma_padded"] + 8 * emit_step.nrow_phys(L) // 2, nconst=wmeta["nconst"])
+                    meta["dfma_node_full"] = 2 * meta["dfma_node"]
+                    cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
+                          '#define SFB_NAME sfb_launch_step_%s\n#define SFB_WTAB_INC "gen/wtab_L%d_%s.inc"\n'
+                          '#include "sfb_step_wloop.cuh"\n' % (L, dd, TN, MINB, tag, L, "ddrx" if dd else "lrot"))
+                    path = os.path.join(GEN, "step_%s.cu" % tag)
+                    _write_if_changed(path, cu)
+                    units.append(path)
+                    meta["tag"] = tag
+                    meta["variant"] = vid
+                    metas.append(meta)
+                    continue
                 if R == -2:      # table-driven loop kernel (two lanes per node); MINB field = CTAs/SM, "chN" = rows per chunk
                     ch = max([int(x[2:]) for x in parts[1:] if x.startswith("ch")] + [2])
                     tabsrc, meta = emit_step.emit_loop_table(L, dd, ch)
@@ -263,7 +285,11 @@ def _deps_hash(src):
     files += [os.path.join(HERE, "..", "include", "specfab_b200.h")]
     if "step_" in os.path.basename(src):
         tag = os.path.basename(src)[5:-3]
-        files.append(os.path.join(GEN, "apply_%s.inc" % tag))
+        if os.path.exists(os.path.join(GEN, "apply_%s.inc" % tag)):
+            files.append(os.path.join(GEN, "apply_%s.inc" % tag))
+        base = tag.split("_v")[0]
+        if os.path.exists(os.path.join(GEN, "wtab_%s.inc" % base)):
+            files.append(os.path.join(GEN, "wtab_%s.inc" % base))
         if os.path.exists(os.path.join(GEN, "apply_%s_full.inc" % tag)):
             files.append(os.path.join(GEN, "apply_%s_full.inc" % tag))
     else:

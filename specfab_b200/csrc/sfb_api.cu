@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,6 +43,48 @@ cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2*
 cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
                            int* status, cudaStream_t st, int red = 0);
+
+// ---- queues of general-state tiles (sfb_common.cuh) ----
+namespace {
+struct WorkList { int* buf = nullptr; long long cap = 0; };
+std::mutex g_wl_mu;
+std::map<std::pair<int, cudaStream_t>, WorkList> g_wl;
+}  // namespace
+cudaError_t sfb_worklist_get(cudaStream_t st, long long ntile, int** buf) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_wl_mu);
+    WorkList& w = g_wl[std::make_pair(dev, st)];
+    if (w.cap < ntile) {
+        if (w.buf) {                       // kernels of earlier launches on this stream may still use the old queue
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            cudaFree(w.buf);
+            w.buf = nullptr; w.cap = 0;
+        }
+        long long cap = 4096;
+        while (cap < ntile) cap *= 2;
+        e = cudaMalloc(&w.buf, (size_t)cap * sizeof(int));
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(w.buf, 0, (size_t)cap * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        w.cap = cap;
+    }
+    *buf = w.buf;
+    return cudaSuccess;
+}
+void sfb_worklist_release() {
+    std::lock_guard<std::mutex> lk(g_wl_mu);
+    for (auto& kv : g_wl) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(kv.first.first);
+        cudaFree(kv.second.buf);
+        cudaSetDevice(cur);
+    }
+    g_wl.clear();
+}
 
 struct SfbStepEntry {
     int L, ddrx, variant, R, TN, dfma_node;
@@ -158,6 +201,7 @@ void sfb_finalize(void) {
     std::lock_guard<std::mutex> lk(g.mu);
     g_stage.release();
     sfb_ops_release();
+    sfb_worklist_release();
     g.L = 0; g.n = 0;
 }
 

@@ -36,3 +36,9 @@ struct SfbRegConst {
 };
 
 typedef cudaError_t (*sfb_step_launch_fn)(const SfbStepParams&, const SfbRegConst&, cudaStream_t);
+
+// Per (device, stream) queue of tiles a fast step kernel hands to its general-state twin (sfb_step_wloop.cuh); owned by
+// sfb_api.cu, grown on demand (synchronises the stream when it has to reallocate), released by sfb_finalize.
+// One int flag per tile, rewritten by the fast kernel on every launch.
+cudaError_t sfb_worklist_get(cudaStream_t st, long long ntile, int** buf);
+void sfb_worklist_release();

@@ -68,6 +68,16 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if len(sys.argv) > 2:
         V = [int(x) for x in sys.argv[2].split(",")]
+    if which == "w":        # windowed loop kernels (variants 60+) against the defaults, physical / general / reduced-form states
+        for terms in (("lrot", "ddrx", "reg"), ("lrot", "reg")):
+            for scheme in ("euler", "rk4"):
+                run(8, 1_000_000, terms, scheme, V, steps=10)
+        run(8, 200_000, ("lrot", "ddrx", "reg"), "euler", V, steps=5, physical=False)
+        run(8, 200_000, ("lrot", "ddrx", "reg"), "rk4", V, steps=5, physical=False)
+        run(8, 200_000, ("lrot", "reg"), "rk4", V, steps=5, physical=False)
+        run(8, 1_000_003, ("lrot", "ddrx", "reg"), "euler", V, steps=5, reduced=True)
+        run(8, 1_000_003, ("lrot", "ddrx", "reg"), "rk4", V, steps=5, reduced=True)
+        run(8, 1_000_003, ("lrot", "reg"), "rk4", V, steps=5, reduced=True)
     if which == "8xr":      # headline kernels on reduced-form states
         run(8, 1_000_000, ("lrot", "reg"), "rk4", V, steps=20, reduced=True)
         run(8, 1_000_000, ("lrot", "reg"), "euler", V, steps=20, reduced=True)
