@@ -65,9 +65,9 @@ EXTRA = {
 # variants under test (SFB_EXP_VARIANTS=1)
 EXP = {
     # windowed loop kernel: (variant, -6, one-warp tiles per CTA, register cap)
-    (8, 1): [(60, -6, 1, 168, "", False), (61, -6, 1, 255, "", False), (62, -6, 1, 200, "", False), (63, -6, 1, 232, "", False), (64, -6, 4, 255, "", False),
-             (65, -6, 1, 184, "", False), (66, -6, 4, 168, "", False)],
-    (8, 0): [(60, -6, 1, 168, "", False), (61, -6, 1, 128, "", False), (62, -6, 4, 168, "", False)],
+    (8, 1): [(60, -6, 1, 168, "", False), (61, -6, 1, 255, "", False), (62, -6, 1, 200, "", False), (63, -6, 1, 232, "", False),
+             (70, -6, 1, 168, "+split", False), (71, -6, 1, 128, "+split", False), (72, -6, 1, 144, "+split", False), (73, -6, 1, 200, "+split", False)],
+    (8, 0): [(60, -6, 1, 168, "", False), (61, -6, 1, 128, "", False), (70, -6, 1, 128, "+split", False), (71, -6, 1, 96, "+split", False)],
     # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
@@ -169,7 +169,9 @@ def generate(Ls):
                                 dfma_node=sum(p.dfma for p in emit_step.plan(L, dd)[1]),
                                 dfma_executed=wmeta["dfma_padded"] + 8 * emit_step.nrow_phys(L) // 2, nconst=wmeta["nconst"])
                     meta["dfma_node_full"] = 2 * meta["dfma_node"]
-                    cu = ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
+                    split = "split" in cmode.split("+")
+                    meta["split"] = int(split)
+                    cu = ('#define SFB_SPLIT %d\n' % int(split)) + ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
                           '#define SFB_NAME sfb_launch_step_%s\n#define SFB_WTAB_INC "gen/wtab_L%d_%s.inc"\n'
                           '#include "sfb_step_wloop.cuh"\n' % (L, dd, TN, MINB, tag, L, "ddrx" if dd else "lrot"))
                     path = os.path.join(GEN, "step_%s.cu" % tag)
