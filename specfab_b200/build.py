@@ -68,6 +68,7 @@ EXP = {
     (8, 1): [(60, -6, 1, 168, "", False), (61, -6, 1, 255, "", False), (62, -6, 1, 200, "", False), (63, -6, 1, 232, "", False),
              (70, -6, 1, 168, "+split", False), (71, -6, 1, 128, "+split", False), (72, -6, 1, 144, "+split", False), (73, -6, 1, 200, "+split", False)],
     (8, 0): [(60, -6, 1, 168, "", False), (61, -6, 1, 128, "", False), (70, -6, 1, 128, "+split", False), (71, -6, 1, 96, "+split", False)],
+    (12, 1): [(70, -6, 1, 168, "+split", False), (71, -6, 1, 200, "+split", False)],
     # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node

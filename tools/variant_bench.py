@@ -68,6 +68,11 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if len(sys.argv) > 2:
         V = [int(x) for x in sys.argv[2].split(",")]
+    if which == "one":      # one L N terms scheme variants [physical(1/0)] [reduced(0/1)]
+        L, N, terms, scheme = int(sys.argv[2]), int(sys.argv[3]), tuple(sys.argv[4].split("+")), sys.argv[5]
+        V = [int(x) for x in sys.argv[6].split(",")]
+        run(L, N, terms, scheme, V, steps=10, physical=(len(sys.argv) <= 7 or sys.argv[7] == "1"), reduced=(len(sys.argv) > 8 and sys.argv[8] == "1"))
+        sys.exit(0)
     if which == "w":        # windowed loop kernels (variants 60+) against the defaults, physical / general / reduced-form states
         for terms in (("lrot", "ddrx", "reg"), ("lrot", "reg")):
             for scheme in ("euler", "rk4"):
