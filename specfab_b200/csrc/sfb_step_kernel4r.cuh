@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, SFB_MINB) step_kernel_rr(const SfbSt
 }  // namespace
 
 extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
+    static std::mutex attr_mu;
     static bool attr_done[64] = {false};
     const size_t fixed = (size_t)kNF * kTNR * 16 + (size_t)kNSc * kTNR * 8 + 16;
     const size_t per_buf = (size_t)kNRowR * kTNR * 16;
@@ -307,6 +308,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
+    std::unique_lock<std::mutex> attr_lk(attr_mu);
     if (!attr_done[dev]) {
         e = cudaFuncSetAttribute(step_kernel_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
@@ -314,15 +316,21 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         if (e != cudaSuccess) return e;
         attr_done[dev] = true;
     }
+    attr_lk.unlock();
     SfbStepParams P = Pin;
     P.n0_global = 1;
     const int nbuf = P.nstage == 1 ? 1 : nbuf_rk;
     const size_t smem = nbuf * per_buf + fixed;
     {
+        // uploaded once per device under a lock, and WAITED for: a later launch on another stream carries no dependency on this copy
+        static std::mutex reg_mu;
         static SfbRegConst last[64];
         static bool have[64] = {false};
+        std::lock_guard<std::mutex> reg_lk(reg_mu);
         if (!have[dev] || memcmp(&last[dev], &reg, sizeof(SfbRegConst)) != 0) {
             e = cudaMemcpyToSymbolAsync(c_reg, &reg, sizeof(SfbRegConst), 0, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return e;
             last[dev] = reg;
             have[dev] = true;

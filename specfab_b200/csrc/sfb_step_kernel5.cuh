@@ -18,6 +18,7 @@
 //   SFB_L, SFB_DDRX (0/1), SFB_TN, SFB_MINB, SFB_WINDOW (0/1), SFB_NAME (launcher symbol), SFB_APPLY_INC
 #pragma once
 #include <cstring>
+#include <mutex>
 #include "sfb_common.cuh"
 #include "sfb_moments.cuh"
 
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const SfbStepParams P
 }  // namespace
 
 extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg, cudaStream_t st) {
+    static std::mutex attr_mu;
     static bool attr_done[64] = {false};
     static int grid_max[64] = {0};
     const size_t fixed = (size_t)2 * kNF * kTN * 16 + (size_t)kNSc * kTN * 8 + (size_t)2 * kNRaw * kTN * 8 + 32;
@@ -356,6 +358,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
+    std::unique_lock<std::mutex> attr_lk(attr_mu);
     if (!attr_done[dev]) {
         e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return e;
@@ -364,6 +367,7 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
         grid_max[dev] = nsm > 0 ? nsm : 148;
         attr_done[dev] = true;
     }
+    attr_lk.unlock();
     if (Pin.rio) return cudaErrorNotSupported;      // reduced-form arrays: reduced kernels only
     SfbStepParams P = Pin;
     P.n0_global = 1;
@@ -373,10 +377,15 @@ extern "C" cudaError_t SFB_NAME(const SfbStepParams& Pin, const SfbRegConst& reg
     const size_t smem = nbuf * per_buf + fixed;
     if (smem > lim) return cudaErrorInvalidConfiguration;
     {
+        // uploaded once per device under a lock, and WAITED for: a later launch on another stream carries no dependency on this copy
+        static std::mutex reg_mu;
         static SfbRegConst last[64];
         static bool have[64] = {false};
+        std::lock_guard<std::mutex> reg_lk(reg_mu);
         if (!have[dev] || memcmp(&last[dev], &reg, sizeof(SfbRegConst)) != 0) {
             e = cudaMemcpyToSymbolAsync(c_reg, &reg, sizeof(SfbRegConst), 0, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return e;
             last[dev] = reg;
             have[dev] = true;
