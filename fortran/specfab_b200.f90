@@ -32,6 +32,14 @@ module specfab_b200
             integer(c_int64_t), value :: N, ld
             type(sfb_step_opts), intent(in) :: opts
         end function
+        ! one host array sharded over several GPUs (contiguous node ranges, one host thread + staging ring per device)
+        integer(c_int) function sfb_step_arr_multi(nlm_in, nlm_out, N, ld, ugrad, tau, opts, devices, ndev) bind(c, name='sfb_step_arr_multi')
+            import; type(c_ptr), value :: nlm_in, nlm_out, ugrad, tau
+            integer(c_int64_t), value :: N, ld
+            type(sfb_step_opts), intent(in) :: opts
+            integer(c_int), intent(in) :: devices(*)
+            integer(c_int), value :: ndev
+        end function
         ! page-lock an existing array once (4x faster host-pointer calls), release before deallocation
         integer(c_int) function sfb_host_register(p, bytes) bind(c, name='sfb_host_register')
             import; type(c_ptr), value :: p; integer(c_int64_t), value :: bytes
@@ -110,8 +118,8 @@ contains
     ! nlm(N,nlm_len) <- one fused step of every node: nlm + dt*matmul(M_LROT+Gamma0*M_DDRX+Lambda*M_CDRX+M_REG, nlm)
     ! batches the loop of src/dynamics.f90:99-110 / src/specfabpy/integrator.py:73-77
     subroutine step_arr(nlm, ugrad, tau, dt, iota, zeta, Gamma0, Lambda, terms, scheme)
-        complex(kind=dp), intent(inout), target :: nlm(:,:)          ! (N, nlm_len)
-        real(kind=dp), intent(in), target       :: ugrad(:,:,:), tau(:,:,:)   ! (N,3,3)
+        complex(kind=dp), intent(inout), target, contiguous :: nlm(:,:)          ! (N, nlm_len); c_loc needs contiguous storage
+        real(kind=dp), intent(in), target, contiguous       :: ugrad(:,:,:), tau(:,:,:)   ! (N,3,3)
         real(kind=dp), intent(in)               :: dt, iota, zeta, Gamma0, Lambda
         integer, intent(in)                     :: terms, scheme
         type(sfb_step_opts) :: o
@@ -120,10 +128,23 @@ contains
                                 c_loc(ugrad), c_loc(tau), o), 'step_arr')
     end subroutine
 
+    ! the same step with the batch sharded over the GPUs listed in devices (0-based CUDA ordinals)
+    subroutine step_arr_multi(nlm, ugrad, tau, dt, iota, zeta, Gamma0, Lambda, terms, scheme, devices)
+        complex(kind=dp), intent(inout), target, contiguous :: nlm(:,:)
+        real(kind=dp), intent(in), target, contiguous       :: ugrad(:,:,:), tau(:,:,:)
+        real(kind=dp), intent(in)               :: dt, iota, zeta, Gamma0, Lambda
+        integer, intent(in)                     :: terms, scheme
+        integer(c_int), intent(in)              :: devices(:)
+        type(sfb_step_opts) :: o
+        o = sfb_step_opts(dt, iota, zeta, 1.0d0, Gamma0, Lambda, c_null_ptr, c_null_ptr, terms, scheme, 1, 0)
+        call check(sfb_step_arr_multi(c_loc(nlm), c_loc(nlm), int(size(nlm,1),c_int64_t), int(size(nlm,1),c_int64_t), &
+                                      c_loc(ugrad), c_loc(tau), o, devices, int(size(devices),c_int)), 'step_arr_multi')
+    end subroutine
+
     ! the same for states kept in reduced form (what src/specfabpy/fenics/CPO.py holds): rnlm(N, rnlm_len), m >= 0 only
     subroutine step_rnlm_arr(rnlm, ugrad, tau, dt, iota, zeta, Gamma0, Lambda, terms, scheme)
-        complex(kind=dp), intent(inout), target :: rnlm(:,:)         ! (N, rnlm_len)
-        real(kind=dp), intent(in), target       :: ugrad(:,:,:), tau(:,:,:)   ! (N,3,3)
+        complex(kind=dp), intent(inout), target, contiguous :: rnlm(:,:)         ! (N, rnlm_len)
+        real(kind=dp), intent(in), target, contiguous       :: ugrad(:,:,:), tau(:,:,:)   ! (N,3,3)
         real(kind=dp), intent(in)               :: dt, iota, zeta, Gamma0, Lambda
         integer, intent(in)                     :: terms, scheme
         type(sfb_step_opts) :: o
@@ -134,7 +155,7 @@ contains
 
     ! drop-in for Eij_tranisotropic_arr (src/specfabpy.f90:474-486)
     function Eij_tranisotropic_arr(nlm, e1,e2,e3, Eij_grain,alpha,n_grain) result(Eij)
-        complex(kind=dp), intent(in), target :: nlm(:,:)
+        complex(kind=dp), intent(in), target, contiguous :: nlm(:,:)
         real(kind=dp), intent(in), target    :: e1(size(nlm,1),3), e2(size(nlm,1),3), e3(size(nlm,1),3)
         real(kind=dp), intent(in)            :: Eij_grain(2), alpha
         integer, intent(in)                  :: n_grain
@@ -146,7 +167,7 @@ contains
 
     ! drop-in for Eij_orthotropic_arr (src/specfabpy.f90:488-500)
     function Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3, e1,e2,e3, Eij_grain,alpha,n_grain) result(Eij)
-        complex(kind=dp), intent(in), target :: nlm_1(:,:), nlm_2(:,:), nlm_3(:,:)
+        complex(kind=dp), intent(in), target, contiguous :: nlm_1(:,:), nlm_2(:,:), nlm_3(:,:)
         real(kind=dp), intent(in), target    :: e1(size(nlm_1,1),3), e2(size(nlm_1,1),3), e3(size(nlm_1,1),3)
         real(kind=dp), intent(in)            :: Eij_grain(6), alpha
         integer, intent(in)                  :: n_grain
@@ -158,7 +179,7 @@ contains
 
     ! drop-in for E_CAFFE_arr (src/specfabpy.f90:543-554)
     function E_CAFFE_arr(nlm, eps, Emin, Emax, n_grain) result(E)
-        complex(kind=dp), intent(in), target :: nlm(:,:)
+        complex(kind=dp), intent(in), target, contiguous :: nlm(:,:)
         real(kind=dp), intent(in), target    :: eps(size(nlm,1),3,3)
         real(kind=dp), intent(in)            :: Emin, Emax
         integer, intent(in)                  :: n_grain
@@ -169,19 +190,19 @@ contains
 
     ! scalar forms keep the reference signatures (N = 1 batches)
     function a2(nlm) result(res)                                   ! src/moments.f90:37
-        complex(kind=dp), intent(in), target :: nlm(:)
+        complex(kind=dp), intent(in), target, contiguous :: nlm(:)
         real(kind=dp), target :: res(3,3)
         call check(sfb_a2_arr(c_loc(nlm), 1_c_int64_t, 1_c_int64_t, c_loc(res)), 'a2')
     end function
 
     function a4(nlm) result(res)                                   ! src/moments.f90:46
-        complex(kind=dp), intent(in), target :: nlm(:)
+        complex(kind=dp), intent(in), target, contiguous :: nlm(:)
         real(kind=dp), target :: res(3,3,3,3)
         call check(sfb_a4_arr(c_loc(nlm), 1_c_int64_t, 1_c_int64_t, c_loc(res)), 'a4')
     end function
 
     subroutine eig(nlm, ei, lami)                                  ! src/frames.f90:14
-        complex(kind=dp), intent(in), target :: nlm(:)
+        complex(kind=dp), intent(in), target, contiguous :: nlm(:)
         real(kind=dp), intent(out), target   :: ei(3,3), lami(3)
         call check(sfb_eig_arr(c_loc(nlm), 1_c_int64_t, 1_c_int64_t, c_loc(ei), c_loc(lami)), 'eig')
     end subroutine

@@ -18,6 +18,13 @@
  * void*, may be NULL) and are asynchronous; the others take HOST pointers, stage through device
  * memory on the current CUDA device and return when the result is in the output buffers.
  * There is no CPU fallback: without a usable CUDA device every call returns SFB_ECUDA.
+ *
+ * Threading (the reference is single threaded and not re-entrant: module globals src/header.f90:16, SAVE'd locals
+ * src/homogenizations.f90:80).  sfb_init / sfb_finalize / sfb_set_variant change process-wide state and must not run
+ * concurrently with any other call.  Between them every entry point may be called from several host threads on distinct
+ * buffers: `_dev` calls are re-entrant (give each thread its own stream); host-pointer calls on the same device take turns
+ * on that device's staging ring, host-pointer calls on different devices (sfb_set_device per thread, or
+ * sfb_step_arr_multi) run concurrently.  sfb_last_error() reports the calling thread's last failure.
  */
 #ifndef SPECFAB_B200_H
 #define SPECFAB_B200_H
@@ -66,19 +73,41 @@ typedef struct sfb_step_opts {
     int32_t terms;      /* SFB_LROT | SFB_DDRX | SFB_CDRX | SFB_REG */
     int32_t scheme;     /* SFB_EULER | SFB_RK4 */
     int32_t nsteps;     /* number of consecutive steps with the same forcing (>= 1) */
-    int32_t reserved;
+    int32_t reserved;   /* flags: 0, or SFB_STEP_GENERAL (see sfb_step_arr) */
 } sfb_step_opts;
 
 /* Fused batched time step:  nlm <- nlm + dt * (M_LROT + gamma0*M_DDRX + lambda*M_CDRX + M_REG) nlm
  * Replaces the per-node loop  M = sf.M_LROT(..) + sf.M_REG(..) + ..; nlm + dt*matmul(M,nlm)
  * (src/specfabpy/integrator.py:73-77, src/dynamics.f90:99-110, src/specfabpy/fenics/CPO.py:200-202).
  * D, W are the symmetric / antisymmetric parts of ugrad; tau may be NULL (then tau := D, as
- * src/specfabpy/integrator.py:39).  nlm_in may equal nlm_out (in-place). */
+ * src/specfabpy/integrator.py:39).  nlm_in may equal nlm_out (in-place).
+ *
+ * Real-valued ODFs and general complex vectors.  The reference operators are plain linear maps on arbitrary complex vectors.
+ * Every physical state has the real-ODF symmetry n_l^-m = (-1)^m conj(n_l^m), Im n_l^0 = 0, which the operators preserve, and
+ * the default kernels exploit it: a 32-node tile whose input has the symmetry to round-off (every component of the defect
+ * within 2^-46 |n_0^0|) is advanced from its rows m >= 0 only and its output is EXACTLY symmetric (the defect, <= 1.4e-14
+ * relative, is projected out); a tile with any node outside that bound takes the general path, which keeps an antisymmetric
+ * part.  A node with a defect below the bound can therefore differ at the 1e-14 level depending on which nodes share its tile
+ * (batch order, chunking, device split).  Callers that need results independent of the batching -- or that deliberately
+ * carry a tiny antisymmetric part -- set SFB_STEP_GENERAL in sfb_step_opts.reserved: every tile then takes the general path. */
+#define SFB_STEP_GENERAL 1   /* sfb_step_opts.reserved: treat every state as a general complex vector */
 int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
                  const double* ugrad, const double* tau, const sfb_step_opts* opts);
 int sfb_step_arr_dev(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld_in, int64_t ld_out,
                      const double* ugrad, int64_t ld_u, const double* tau, int64_t ld_t,
                      const sfb_step_opts* opts, void* stream);
+
+/* One host array on SEVERAL GPUs of this process (SURVEY.md 8b "multi-GPU selection via explicit device list", 8e): the nodes
+ * are split into contiguous ranges on 32-node boundaries, range i goes to devices[i]; one host thread, one staging ring and
+ * three streams per device, no inter-GPU traffic (every node is independent: src/dynamics.f90:52,251, the per-node loops of
+ * src/specfabpy.f90:483-485).  This is the entry point for the reference's single-process callers (Fortran programs, f2py,
+ * an Elmer rank): same arguments as sfb_step_arr plus the device ordinals.  The result is bit-identical to the one-device
+ * call; the calling thread's current device is restored.  sfb_init must have been called once (it holds no per-device state
+ * the step needs). */
+int sfb_step_arr_multi(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld, const double* ugrad, const double* tau,
+                       const sfb_step_opts* opts, const int* devices, int ndev);
+int sfb_step_rnlm_arr_multi(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld, const double* ugrad, const double* tau,
+                            const sfb_step_opts* opts, const int* devices, int ndev);
 
 /* The same fused step on REDUCED-FORM states: rnlm(N, rnlm_len) holds the m >= 0 coefficients of a real-valued ODF, row
  * (l, m) at (l/2)^2 + m -- the layout of nlm_to_rnlm / rnlm_to_nlm (src/reducedform.f90:160-187, src/specfabpy.f90:1076-1094),
@@ -135,6 +164,14 @@ int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const do
                               const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status);
 int sfb_Eij_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* e1, const double* e2, const double* e3,
                                   const double* Eij_grain, double alpha, int n_grain, double* Eij, int32_t* status, void* stream);
+/* Evw_tranisotropic(nlm, v, w, tau, Eij_grain, alpha, n_grain) -> Evw, batched over nodes: v, w (N,3), tau (N,3,3), Evw (N)
+ *                                            src/specfabpy.f90:379-388, src/enhancementfactors.f90:47-69.
+ * The generalized enhancement factor for an ARBITRARY direction pair and stress (Eij_tranisotropic is its six eigenframe
+ * pairs with tau_vv / tau_vw, src/enhancementfactors.f90:398-413).  n_grain = 1 or -3 (n' = 3 through Eij_tranisotropic_arr). */
+int sfb_Evw_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* v, const double* w, const double* tau,
+                              const double* Eij_grain, double alpha, int n_grain, double* Evw, int32_t* status);
+int sfb_Evw_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* v, const double* w, const double* tau,
+                                  const double* Eij_grain, double alpha, int n_grain, double* Evw, int32_t* status, void* stream);
 /* Fused a2 -> eigenframe -> Eij_tranisotropic in that frame (the eigenenhancements); batches
  * src/specfabpy/fenics/enhancementfactor.py:101-128 / src/specfabpy/common.py:13-37.  ei/lami optional outputs. */
 int sfb_Eij_eigenframe_arr(const double* nlm, int64_t N, int64_t ld, const double* Eij_grain, double alpha, int n_grain,

@@ -70,8 +70,12 @@ def _scheme(s):
     return {"euler": SFB_EULER, "rk4": SFB_RK4}[str(s).lower()]
 
 
-def _opts(dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, g0_ptr=None, lam_ptr=None):
+SFB_STEP_GENERAL = 1       # sfb_step_opts.reserved flag (include/specfab_b200.h)
+
+
+def _opts(dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, g0_ptr=None, lam_ptr=None, general=False):
     o = StepOpts()
+    o.reserved = SFB_STEP_GENERAL if general else 0
     o.dt, o.iota, o.zeta, o.nu_mult = float(dt), float(iota), float(zeta), float(nu)
     o.gamma0 = 0.0 if g0_ptr else float(Gamma0)
     o.lambda_ = 0.0 if lam_ptr else float(Lambda)
@@ -88,27 +92,32 @@ def _farr(a, dtype, shape_tail):
 
 
 def step_arr(nlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.0, Lambda=0.0,
-             terms=("lrot", "reg"), scheme="euler", nsteps=1, out=None):
+             terms=("lrot", "reg"), scheme="euler", nsteps=1, out=None, devices=None, general=False):
     """Batched fused time step of N independent nodes (host arrays).
+
+    devices: list of CUDA device ordinals -> the batch is sharded over these GPUs by contiguous node range
+    (sfb_step_arr_multi: one host thread and staging ring per device); None = the current device.
+    general=True: treat every state as a general complex vector (SFB_STEP_GENERAL: no real-ODF shortcut, results
+    independent of how nodes are batched).
 
     nlm (N,nlm_len) complex128, ugrad (N,3,3), tau (N,3,3) or None (tau := sym(ugrad)).
     Gamma0 / Lambda: scalars or (N,) arrays.  Returns the new nlm (N,nlm_len), Fortran-ordered
     (written into `out` when given: a Fortran-ordered (N,nlm_len) complex128 array, e.g. pinned memory).
     Batches  nlm + dt*matmul(M_LROT + Gamma0*M_DDRX + Lambda*M_CDRX + M_REG, nlm)
     (reference per node: src/specfabpy/integrator.py:73-77, src/dynamics.f90:99-110)."""
-    return _step_host(False, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out)
+    return _step_host(False, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out, devices, general)
 
 
 def step_rnlm_arr(rnlm, ugrad, tau=None, dt=0.0, iota=1.0, zeta=0.0, nu=1.0, Gamma0=0.0, Lambda=0.0,
-                  terms=("lrot", "reg"), scheme="euler", nsteps=1, out=None):
+                  terms=("lrot", "reg"), scheme="euler", nsteps=1, out=None, devices=None):
     """step_arr on REDUCED-FORM states: rnlm (N, rnlm_len) complex128 holds the m >= 0 coefficients of a real-valued ODF
     (nlm_to_rnlm / rnlm_to_nlm, src/reducedform.f90:160-187 -- the state representation of the FE couplers,
     src/specfabpy/fenics/CPO.py).  Same arguments and result as step_arr with every state array in reduced form;
     equals nlm_to_rnlm_arr(step_arr(rnlm_to_nlm_arr(rnlm), ...)) bit for bit and moves 25/45 (L=8) of the state bytes."""
-    return _step_host(True, rnlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out)
+    return _step_host(True, rnlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out, devices, False)
 
 
-def _step_host(reduced, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out):
+def _step_host(reduced, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, terms, scheme, nsteps, out, devices=None, general=False):
     n = _need_init()
     lib = _lib.load()
     if reduced:
@@ -121,6 +130,8 @@ def _step_host(reduced, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, ter
     ta = None
     if tau is not None:
         ta = _farr(tau, np.float64, (3, 3))
+        if ta.shape[0] != N:
+            raise ValueError("tau has %d nodes, nlm has %d" % (ta.shape[0], N))
     keep = []
 
     def vec(x):
@@ -133,11 +144,16 @@ def _step_host(reduced, nlm, ugrad, tau, dt, iota, zeta, nu, Gamma0, Lambda, ter
         return v.ctypes.data
 
     o = _opts(dt, iota, zeta, nu, 0.0 if np.ndim(Gamma0) else Gamma0, 0.0 if np.ndim(Lambda) else Lambda,
-              terms, scheme, nsteps, vec(Gamma0), vec(Lambda))
+              terms, scheme, nsteps, vec(Gamma0), vec(Lambda), general)
     if out is None:
         out = np.empty((N, n), dtype=np.complex128, order="F")
     elif out.shape != (N, n) or out.dtype != np.complex128 or not out.flags.f_contiguous:
         raise ValueError("out must be a Fortran-ordered complex128 array of shape (N, %s)" % ("rnlm_len" if reduced else "nlm_len"))
+    if devices is not None:
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        _lib.check((lib.sfb_step_rnlm_arr_multi if reduced else lib.sfb_step_arr_multi)(
+            nlm_f.ctypes.data, out.ctypes.data, N, N, ug.ctypes.data, ta.ctypes.data if ta is not None else None, C.byref(o), devs, len(devices)))
+        return out
     _lib.check((lib.sfb_step_rnlm_arr if reduced else lib.sfb_step_arr)(nlm_f.ctypes.data, out.ctypes.data, N, N, ug.ctypes.data,
                                 ta.ctypes.data if ta is not None else None, C.byref(o)))
     return out
@@ -496,6 +512,8 @@ def Eij_tranisotropic_arr(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_sta
     x = _nlm15(nlm, 45 if int(n_grain) == 3 else 15)
     N = x.shape[0]
     es = [_farr(e, np.float64, (3,)) for e in (e1, e2, e3)]
+    if any(e.shape[0] != N for e in es):
+        raise ValueError("e1, e2, e3 must have one row per node of nlm (%d)" % N)
     g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
     if g.shape != (2,):
         raise ValueError("Eij_grain must have 2 entries (Emm, Emt)")
@@ -504,6 +522,31 @@ def Eij_tranisotropic_arr(nlm, e1, e2, e3, Eij_grain, alpha, n_grain, return_sta
     _lib.check(_lib.load().sfb_Eij_tranisotropic_arr(x.ctypes.data, N, N, es[0].ctypes.data, es[1].ctypes.data, es[2].ctypes.data,
                                                      g.ctypes.data, float(alpha), int(n_grain), out.ctypes.data, st.ctypes.data))
     return (out, st) if return_status else out
+
+
+def Evw_tranisotropic_arr(nlm, v, w, tau, Eij_grain, alpha, n_grain, return_status=False):
+    """Evw_tranisotropic batched over nodes: nlm (N,nlm_len), v, w (N,3), tau (N,3,3) -> Evw (N,)
+    reference (per node): src/specfabpy.f90:379-388, src/enhancementfactors.f90:47-69.  n_grain: 1 or -3."""
+    _need_init()
+    x = _nlm15(nlm, 15)
+    N = x.shape[0]
+    vv, ww, tt = _farr(v, np.float64, (3,)), _farr(w, np.float64, (3,)), _farr(tau, np.float64, (3, 3))
+    if vv.shape[0] != N or ww.shape[0] != N or tt.shape[0] != N:
+        raise ValueError("v, w, tau must have one entry per node of nlm (%d)" % N)
+    g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
+    if g.shape != (2,):
+        raise ValueError("Eij_grain must have 2 entries (Emm, Emt)")
+    out = np.empty(N, dtype=np.float64)
+    st = np.zeros(N, dtype=np.int32)
+    _lib.check(_lib.load().sfb_Evw_tranisotropic_arr(x.ctypes.data, N, N, vv.ctypes.data, ww.ctypes.data, tt.ctypes.data, g.ctypes.data,
+                                                     float(alpha), int(n_grain), out.ctypes.data, st.ctypes.data))
+    return (out, st) if return_status else out
+
+
+def Evw_tranisotropic(nlm, v, w, tau, Eij_grain, alpha, n_grain):
+    """scalar form with the reference's f2py signature (src/specfabpy.f90:379)"""
+    return float(Evw_tranisotropic_arr(np.asarray(nlm)[None, :], np.asarray(v, float)[None, :], np.asarray(w, float)[None, :],
+                                       np.asarray(tau, float)[None, :, :], Eij_grain, alpha, n_grain)[0])
 
 
 def Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij_grain, alpha, n_grain):
@@ -516,6 +559,8 @@ def Eij_orthotropic_arr(nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij_grain, alpha, n_gra
     if x2.shape[0] != N or (x3 is not None and x3.shape[0] != N):
         raise ValueError("nlm_1, nlm_2, nlm_3 must have the same number of nodes")
     es = [_farr(e, np.float64, (3,)) for e in (e1, e2, e3)]
+    if any(e.shape[0] != N for e in es):
+        raise ValueError("e1, e2, e3 must have one row per node of nlm (%d)" % N)
     g = np.ascontiguousarray(Eij_grain, dtype=np.float64)
     if g.shape != (6,):
         raise ValueError("Eij_grain must have 6 entries (Ebb, Enn, Evv, Env, Ebv, Enb)")

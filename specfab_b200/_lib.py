@@ -42,6 +42,8 @@ SIGNATURES = {
     "sfb_step_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, C.POINTER(StepOpts), _P]),
     "sfb_apply_bounds_rnlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "sfb_step_rnlm_arr": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(StepOpts)]),
+    "sfb_step_arr_multi": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(StepOpts), C.POINTER(C.c_int), C.c_int]),
+    "sfb_step_rnlm_arr_multi": (C.c_int, [_P, _P, _I64, _I64, _P, _P, C.POINTER(StepOpts), C.POINTER(C.c_int), C.c_int]),
     "sfb_step_rnlm_arr_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _I64, C.POINTER(StepOpts), _P]),
     "sfb_a2_arr": (C.c_int, [_P, _I64, _I64, _P]),
     "sfb_a2_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
@@ -53,6 +55,8 @@ SIGNATURES = {
     "sfb_eigframe_arr_dev": (C.c_int, [_P, _I64, _I64, C.c_char_p, _P, _P, _P]),
     "sfb_Eij_tranisotropic_arr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
     "sfb_Eij_tranisotropic_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P]),
+    "sfb_Evw_tranisotropic_arr": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P]),
+    "sfb_Evw_tranisotropic_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P]),
     "sfb_a6_arr": (C.c_int, [_P, _I64, _I64, _P]),
     "sfb_a6_arr_dev": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "sfb_E_CAFFE_arr": (C.c_int, [_P, _I64, _I64, _P, C.c_double, C.c_double, C.c_int, _P]),

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sfb_common.cuh"
@@ -43,6 +44,8 @@ cudaError_t sfb_launch_eij_orth(const double2* q1, long long ld1, const double2*
 cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const double* e1, const double* e2, const double* e3,
                            long long lde, const sfb::EijCoef& K, double* Eij, long long ldo, double* ei_out, double* lam_out,
                            int* status, cudaStream_t st, int red = 0);
+cudaError_t sfb_launch_evw(const double2* nlm, long long N, long long ld, const double* v, const double* w, const double* tau, long long lde,
+                           const sfb::EijCoef& K, double* Evw, int* status, cudaStream_t st);
 
 // ---- queues of general-state tiles (sfb_common.cuh) ----
 namespace {
@@ -102,16 +105,21 @@ struct State {
     std::mutex mu;
 } g;
 
+// Error text is per thread (sfb_last_error reports the calling thread's last failure); the process-wide copy of the most
+// recent message -- what a caller on another thread falls back to -- is only touched under its own lock.
 thread_local std::string t_err;
+std::mutex g_err_mu;
 
 int fail(int code, const std::string& msg) {
     t_err = msg;
+    std::lock_guard<std::mutex> lk(g_err_mu);
     g.err = msg;
     return code;
 }
 int cuda_fail(cudaError_t e, const char* what) {
     return fail(SFB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+int cuda_rc(cudaError_t e, const char* what) { return e == cudaSuccess ? SFB_OK : cuda_fail(e, what); }
 #define CK(call)                                          \
     do {                                                  \
         cudaError_t e__ = (call);                         \
@@ -157,13 +165,23 @@ struct Staging {
         dev = -1;
     }
 };
-Staging g_stage;
+// one staging ring and one lock per device: host-pointer calls on different devices (sfb_step_arr_multi, or a caller's own
+// threads after sfb_set_device) run concurrently; calls on the same device take turns
+constexpr int kMaxDev = 64;
+Staging g_stage[kMaxDev];
+std::mutex g_stage_mu[kMaxDev];
 
 }  // namespace
 
 extern "C" {
 
-const char* sfb_last_error(void) { return t_err.empty() ? g.err.c_str() : t_err.c_str(); }
+const char* sfb_last_error(void) {
+    if (t_err.empty()) {          // nothing failed on this thread: hand out a private copy of the process-wide message
+        std::lock_guard<std::mutex> lk(g_err_mu);
+        t_err = g.err;
+    }
+    return t_err.c_str();
+}
 
 int sfb_init(int L) {
     std::lock_guard<std::mutex> lk(g.mu);
@@ -199,7 +217,15 @@ int sfb_get_lm(int32_t* lm) {
 
 void sfb_finalize(void) {
     std::lock_guard<std::mutex> lk(g.mu);
-    g_stage.release();
+    {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (int d = 0; d < kMaxDev; ++d) {
+            std::lock_guard<std::mutex> sl(g_stage_mu[d]);
+            if (g_stage[d].dev >= 0) { cudaSetDevice(d); g_stage[d].release(); }
+        }
+        cudaSetDevice(cur);
+    }
     sfb_ops_release();
     sfb_worklist_release();
     g.L = 0; g.n = 0;
@@ -226,6 +252,7 @@ static int check_opts(const sfb_step_opts* o) {
     if (o->scheme != SFB_EULER && o->scheme != SFB_RK4) return fail(SFB_EINVAL, "scheme must be SFB_EULER or SFB_RK4");
     if (o->nsteps < 1) return fail(SFB_EINVAL, "nsteps must be >= 1");
     if (o->terms & ~(SFB_LROT | SFB_DDRX | SFB_CDRX | SFB_REG)) return fail(SFB_EINVAL, "unknown bits in terms");
+    if (o->reserved & ~SFB_STEP_GENERAL) return fail(SFB_EINVAL, "unknown flag in sfb_step_opts.reserved");
     return SFB_OK;
 }
 
@@ -243,6 +270,12 @@ static int step_dev_impl(const double* nlm_in, double* nlm_out, int64_t N, int64
     const int ddrx = (o->terms & SFB_DDRX) ? 1 : 0;
     if (ddrx && tau && ld_t < N) return fail(SFB_EINVAL, "ld_t < N");
     const SfbStepEntry* ent = find_step(g.L, ddrx, o->scheme == SFB_RK4 ? 4 : 1);
+    if (o->reserved & SFB_STEP_GENERAL) {      // every tile through the general (unreduced) algorithm: the full-form kernels
+        if (rio) return fail(SFB_EINVAL, "SFB_STEP_GENERAL: reduced-form states are real ODFs by construction");
+        ent = nullptr;
+        for (const auto& e : kStepRegistry)
+            if (e.L == g.L && e.ddrx == ddrx && e.variant == 40) ent = &e;
+    }
     if (!ent) return fail(SFB_ENOTBUILT, "step kernel for this L not compiled");
     SfbStepParams P;
     P.rio = rio;
@@ -312,34 +345,44 @@ static int step_host_impl(const double* nlm_in, double* nlm_out, int64_t N, int6
     if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
     if (N == 0) return SFB_OK;
     if (!nlm_in || !nlm_out || !ugrad) return fail(SFB_EINVAL, "null array");
-    std::lock_guard<std::mutex> lk(g.mu);
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    if (g_stage.dev != dev) { g_stage.release(); g_stage.dev = dev; }
+    if (dev < 0 || dev >= kMaxDev) return fail(SFB_EINVAL, "device ordinal out of range");
+    std::lock_guard<std::mutex> lk(g_stage_mu[dev]);
+    Staging& stage = g_stage[dev];
+    stage.dev = dev;
     const int n = rio ? (g.L / 2 + 1) * (g.L / 2 + 1) : g.n;      // coefficient rows that cross PCIe
-    static int64_t chunk_nodes = 0;      // nodes per pipeline stage (H2D | kernel | D2H on rotating streams); SFB_CHUNK overrides
-    if (!chunk_nodes) { const char* ev = getenv("SFB_CHUNK"); chunk_nodes = ev ? atoll(ev) : (1 << 16); if (chunk_nodes < 1024) chunk_nodes = 1024; }
+    static const int64_t chunk_nodes = [] {      // nodes per pipeline stage (H2D | kernel | D2H on rotating streams); SFB_CHUNK overrides
+        const char* ev = getenv("SFB_CHUNK");
+        const int64_t c = ev ? atoll(ev) : (1 << 16);
+        return c < 1024 ? (int64_t)1024 : c;
+    }();
     const int64_t chunk = std::min<int64_t>(N, chunk_nodes);
     const bool ddrx = (o->terms & SFB_DDRX) != 0;
     int slot = 0;
-    for (int64_t p0 = 0; p0 < N; p0 += chunk, slot = (slot + 1) % Staging::kSlots) {
+    rc = SFB_OK;
+    for (int64_t p0 = 0; p0 < N && rc == SFB_OK; p0 += chunk, slot = (slot + 1) % Staging::kSlots) {
         const int64_t c = std::min<int64_t>(chunk, N - p0);
-        Slot& s = g_stage.s[slot];
+        Slot& s = stage.s[slot];
         rc = ensure_slot(s, (size_t)chunk * n * 16, (size_t)chunk);
-        if (rc) return rc;
-        CK(cudaMemcpy2DAsync(s.nin, chunk * 16, nlm_in + 2 * p0, ld * 16, c * 16, n, cudaMemcpyHostToDevice, s.st));
-        CK(cudaMemcpy2DAsync(s.ug, chunk * 8, ugrad + p0, ld * 8, c * 8, 9, cudaMemcpyHostToDevice, s.st));
-        if (ddrx && tau) CK(cudaMemcpy2DAsync(s.tau, chunk * 8, tau + p0, ld * 8, c * 8, 9, cudaMemcpyHostToDevice, s.st));
+        if (rc) break;
+        // a coefficient row of the chunk is one contiguous run of c nodes on both sides: n (or 9) descriptors of c*16 (c*8) bytes
+        rc = cuda_rc(cudaMemcpy2DAsync(s.nin, chunk * 16, nlm_in + 2 * p0, ld * 16, c * 16, n, cudaMemcpyHostToDevice, s.st), "H2D nlm");
+        if (!rc) rc = cuda_rc(cudaMemcpy2DAsync(s.ug, chunk * 8, ugrad + p0, ld * 8, c * 8, 9, cudaMemcpyHostToDevice, s.st), "H2D ugrad");
+        if (!rc && ddrx && tau) rc = cuda_rc(cudaMemcpy2DAsync(s.tau, chunk * 8, tau + p0, ld * 8, c * 8, 9, cudaMemcpyHostToDevice, s.st), "H2D tau");
         sfb_step_opts oo = *o;
-        if (o->gamma0_arr) { CK(cudaMemcpyAsync(s.g0, o->gamma0_arr + p0, c * 8, cudaMemcpyHostToDevice, s.st)); oo.gamma0_arr = s.g0; }
-        if (o->lambda_arr) { CK(cudaMemcpyAsync(s.lam, o->lambda_arr + p0, c * 8, cudaMemcpyHostToDevice, s.st)); oo.lambda_arr = s.lam; }
-        rc = step_dev_impl(s.nin, s.nout, c, chunk, chunk, s.ug, chunk, (ddrx && tau) ? s.tau : nullptr, chunk, &oo, s.st, rio);
-        if (rc) return rc;
-        CK(cudaMemcpy2DAsync(nlm_out + 2 * p0, ld * 16, s.nout, chunk * 16, c * 16, n, cudaMemcpyDeviceToHost, s.st));
+        if (!rc && o->gamma0_arr) { rc = cuda_rc(cudaMemcpyAsync(s.g0, o->gamma0_arr + p0, c * 8, cudaMemcpyHostToDevice, s.st), "H2D gamma0"); oo.gamma0_arr = s.g0; }
+        if (!rc && o->lambda_arr) { rc = cuda_rc(cudaMemcpyAsync(s.lam, o->lambda_arr + p0, c * 8, cudaMemcpyHostToDevice, s.st), "H2D lambda"); oo.lambda_arr = s.lam; }
+        if (!rc) rc = step_dev_impl(s.nin, s.nout, c, chunk, chunk, s.ug, chunk, (ddrx && tau) ? s.tau : nullptr, chunk, &oo, s.st, rio);
+        if (!rc) rc = cuda_rc(cudaMemcpy2DAsync(nlm_out + 2 * p0, ld * 16, s.nout, chunk * 16, c * 16, n, cudaMemcpyDeviceToHost, s.st), "D2H nlm");
     }
-    for (auto& s : g_stage.s)
-        if (s.st) CK(cudaStreamSynchronize(s.st));
-    return SFB_OK;
+    // also on the error path: the slot streams may still be reading from / writing to the caller's arrays
+    for (auto& s : stage.s)
+        if (s.st) {
+            const cudaError_t e = cudaStreamSynchronize(s.st);
+            if (e != cudaSuccess && rc == SFB_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+        }
+    return rc;
 }
 
 int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
@@ -350,6 +393,58 @@ int sfb_step_arr(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld,
 int sfb_step_rnlm_arr(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld,
                       const double* ugrad, const double* tau, const sfb_step_opts* o) {
     return step_host_impl(rnlm_in, rnlm_out, N, ld, ugrad, tau, o, 1);
+}
+
+// One host array sharded over several GPUs of this process: contiguous node ranges [i*N/G, (i+1)*N/G), one host
+// thread + one staging ring (three streams) per device, no inter-GPU traffic.  The reference's callers are single-process
+// programs (src/dynamics.f90:99-110 via Fortran / f2py / Elmer): this is how ONE such process uses all GPUs of the box.
+static int step_multi_impl(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld, const double* ugrad, const double* tau,
+                           const sfb_step_opts* o, const int* devices, int ndev, int rio) {
+    if (!g.L) return fail(SFB_ENOINIT, "sfb_init not called");
+    if (ndev < 1 || !devices) return fail(SFB_EINVAL, "need at least one device");
+    if (N < 0 || ld < N) return fail(SFB_EINVAL, "need 0 <= N <= ld");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    for (int i = 0; i < ndev; ++i) {
+        if (devices[i] < 0 || devices[i] >= count || devices[i] >= kMaxDev) return fail(SFB_EINVAL, "device ordinal out of range");
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) return fail(SFB_EINVAL, "duplicate device in the list");
+    }
+    if (N == 0) return check_opts(o);
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    std::vector<int> rcs(ndev, SFB_OK);
+    std::vector<std::string> errs(ndev);
+    auto work = [&](int i) {
+        // ranges on 32-node boundaries, so that the tiles -- and with them every bit of the result -- do not depend on G
+        const int64_t tiles = (N + 31) / 32;
+        const int64_t p0 = std::min<int64_t>(N, (tiles * i / ndev) * 32), p1 = std::min<int64_t>(N, (tiles * (i + 1) / ndev) * 32);
+        if (p1 <= p0) return;
+        if (cudaSetDevice(devices[i]) != cudaSuccess) { rcs[i] = SFB_ECUDA; errs[i] = "cudaSetDevice failed"; return; }
+        sfb_step_opts oo = *o;
+        if (o->gamma0_arr) oo.gamma0_arr = o->gamma0_arr + p0;
+        if (o->lambda_arr) oo.lambda_arr = o->lambda_arr + p0;
+        rcs[i] = step_host_impl(nlm_in + 2 * p0, nlm_out + 2 * p0, p1 - p0, ld, ugrad + p0, tau ? tau + p0 : nullptr, &oo, rio);
+        if (rcs[i]) errs[i] = t_err;
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < ndev; ++i) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    cudaSetDevice(cur);
+    for (int i = 0; i < ndev; ++i)
+        if (rcs[i]) return fail(rcs[i], "device " + std::to_string(devices[i]) + ": " + errs[i]);
+    return SFB_OK;
+}
+
+int sfb_step_arr_multi(const double* nlm_in, double* nlm_out, int64_t N, int64_t ld, const double* ugrad, const double* tau,
+                       const sfb_step_opts* o, const int* devices, int ndev) {
+    return step_multi_impl(nlm_in, nlm_out, N, ld, ugrad, tau, o, devices, ndev, 0);
+}
+
+int sfb_step_rnlm_arr_multi(const double* rnlm_in, double* rnlm_out, int64_t N, int64_t ld, const double* ugrad, const double* tau,
+                            const sfb_step_opts* o, const int* devices, int ndev) {
+    return step_multi_impl(rnlm_in, rnlm_out, N, ld, ugrad, tau, o, devices, ndev, 1);
 }
 
 int sfb_set_variant(int v) { g_variant = v; return SFB_OK; }
@@ -521,6 +616,39 @@ int sfb_Eij_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const do
                                        Eij_grain, alpha, n_grain, out.as<double>(), ds.as<int32_t>(), nullptr);
     if (rc) return rc;
     CK(cudaMemcpy(Eij, out.p, (size_t)N * 6 * 8, cudaMemcpyDeviceToHost));
+    if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return SFB_OK;
+}
+int sfb_Evw_tranisotropic_arr_dev(const double* nlm, int64_t N, int64_t ld, const double* v, const double* w, const double* tau,
+                                  const double* Eij_grain, double alpha, int n_grain, double* Evw, int32_t* status, void* stream) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    sfb::EijCoef K;
+    if ((rc = make_coef(Eij_grain, alpha, n_grain, K))) return rc;
+    if (n_grain == 3) return fail(SFB_EINVAL, "Evw_tranisotropic_arr: n_grain = 3 is served by Eij_tranisotropic_arr only (n' = 1, -3 here)");
+    if (N == 0) return SFB_OK;
+    if (!v || !w || !tau || !Evw) return fail(SFB_EINVAL, "null array");
+    CK(sfb_launch_evw(reinterpret_cast<const double2*>(nlm), N, ld, v, w, tau, N, K, Evw, status, (cudaStream_t)stream));
+    return SFB_OK;
+}
+int sfb_Evw_tranisotropic_arr(const double* nlm, int64_t N, int64_t ld, const double* v, const double* w, const double* tau,
+                              const double* Eij_grain, double alpha, int n_grain, double* Evw, int32_t* status) {
+    int rc = basic_check(nlm, N, ld);
+    if (rc) return rc;
+    if (N == 0) { sfb::EijCoef K; return make_coef(Eij_grain, alpha, n_grain, K); }
+    if (!v || !w || !tau || !Evw) return fail(SFB_EINVAL, "null array");
+    DevTmp in, dv, out, ds;
+    if ((rc = stage_rows(in, nlm, N, ld, 15))) return rc;
+    CK(dv.alloc((size_t)N * 15 * 8));
+    CK(cudaMemcpy(dv.as<double>(), v, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv.as<double>() + 3 * N, w, (size_t)N * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv.as<double>() + 6 * N, tau, (size_t)N * 9 * 8, cudaMemcpyHostToDevice));
+    CK(out.alloc((size_t)N * 8));
+    CK(ds.alloc((size_t)N * 4));
+    rc = sfb_Evw_tranisotropic_arr_dev(in.as<double>(), N, N, dv.as<double>(), dv.as<double>() + 3 * N, dv.as<double>() + 6 * N,
+                                       Eij_grain, alpha, n_grain, out.as<double>(), ds.as<int32_t>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(Evw, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
     if (status) CK(cudaMemcpy(status, ds.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
     return SFB_OK;
 }

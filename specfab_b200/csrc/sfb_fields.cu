@@ -117,6 +117,28 @@ __global__ void __launch_bounds__(kBlock, MB) eij_kernel(const double2* __restri
     if (status) status[p] = st;
 }
 
+// Evw_tranisotropic batched over nodes (src/specfabpy.f90:379-388): v, w (N,3), tau (N,3,3), one factor per node
+__global__ void __launch_bounds__(kBlock) evw_kernel(const double2* __restrict__ nlm, long long N, long long ld, const double* __restrict__ v,
+                                                     const double* __restrict__ w, const double* __restrict__ tau, long long lde, sfb::EijCoef K,
+                                                     double* __restrict__ Evw, int* __restrict__ status) {
+    const long long p = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= N) return;
+    double2 n00, n2[3], n4[5];
+    load_m_ge0(nlm, ld, p, n00, n2, n4, 0);
+    double vv[3], ww[3], t[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        vv[i] = v[(long long)i * lde + p];
+        ww[i] = w[(long long)i * lde + p];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[i][k] = tau[(long long)(i + 3 * k) * lde + p];
+    }
+    double E;
+    const int st = sfb::evw_tranisotropic(n00, n2, n4, vv, ww, t, K, E);
+    Evw[p] = E;
+    if (status) status[p] = st;
+}
+
 // apply_bounds (src/dynamics.f90:530-557): rescale the l=2 / l=4 blocks if their power spectrum S(l)
 // (src/idealstate.f90:80-93) exceeds that of the delta function; other coefficients pass through.
 __global__ void __launch_bounds__(kBlock) bounds_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long N,
@@ -221,6 +243,12 @@ cudaError_t sfb_launch_eij(const double2* nlm, long long N, long long ld, const 
         else if (mb == 4) eij_kernel<4><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status, red);
         else eij_kernel<2><<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, e1, e2, e3, lde, K, Eij, ldo, ei_out, lam_out, status, red);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t sfb_launch_evw(const double2* nlm, long long N, long long ld, const double* v, const double* w, const double* tau, long long lde,
+                           const sfb::EijCoef& K, double* Evw, int* status, cudaStream_t st) {
+    if (N > 0) evw_kernel<<<nblk(N), kBlock, 0, st>>>(nlm, N, ld, v, w, tau, lde, K, Evw, status);
     return cudaGetLastError();
 }
 

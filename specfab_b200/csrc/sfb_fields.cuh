@@ -427,4 +427,75 @@ __device__ __forceinline__ int eij_tranisotropic(double2 n00, const double2 n2[3
     return status;
 }
 
+// Evw_tranisotropic (src/enhancementfactors.f90:47-69): ONE generalized enhancement factor for an arbitrary pair (v, w) and
+// an arbitrary stress tau, (1 - alpha) * Sachs + alpha * Taylor, each as the ratio to the isotropic response.  Same algebra
+// as one pass of the loop in eij_tranisotropic (kept separate so that the tuned six-pair kernel is not perturbed).
+__device__ __forceinline__ int evw_tranisotropic(double2 n00, const double2 n2[3], const double2 n4[5], const double v[3], const double w[3],
+                                                 const double tau[3][3], const EijCoef& K, double& Evw) {
+    double a2v[6], a4p[21], a2m[3][3];
+    ev_c2_mandel(n00, n2[0], n2[1], n2[2], a2v);
+    ev_c4_mandel(n00, n2, n4, a4p);
+    vec_to_mat(a2v, a2m);
+    double vw[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vw[i][j] = v[i] * w[j];
+    double tv[6];
+    mat_to_vec(tau, tv);
+    // ---- Sachs (src/homogenizations.f90:88-91,115)
+    double a4t_v[6], a4t[3][3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) s += a4p[i <= j ? tri6(i, j) : tri6(j, i)] * tv[j];
+        a4t_v[i] = s;
+    }
+    vec_to_mat(a4t_v, a4t);
+    const double a2tau = dinner22(a2m, tau);
+    double eps[3][3], epsi[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double ac = 0.0, ac2 = 0.0;   // tau.a2 + a2.tau
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { ac += tau[i][k] * a2m[k][j]; ac2 += a2m[i][k] * tau[k][j]; }
+            eps[i][j] = ((1.0 * tau[i][j] - K.sA * a2tau * (i == j ? 1.0 : 0.0)) + K.sB * a4t[i][j]) + K.sC * (ac + ac2);
+            epsi[i][j] = K.s_iso * tau[i][j];
+        }
+    const double Es = dinner22(eps, vw) / dinner22(epsi, vw);
+    // ---- Taylor (src/homogenizations.f90:172-188)
+    int status = 0;
+    double F[6][6], invd[6];
+    {
+        double P[6][6];
+        taylor_P(a2v, a4p, K, P);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (j <= i) F[i][j] = P[i][j];
+    }
+    double x[6];
+    if (potf2_lower(F, invd) == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = tv[i];
+        potrs_lower(F, invd, x);
+    } else {
+        status |= taylor_fallback_solve(a2v, a4p, K, tv, x);
+    }
+    double et[3][3], eti[3][3];
+    vec_to_mat(x, et);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) eti[i][j] = tau[i][j] / K.t_iso;
+    const double Et = dinner22(et, vw) / dinner22(eti, vw);
+    Evw = (1 - K.alpha) * Es + K.alpha * Et;
+    if (!isfinite(Evw)) status |= SFB_ST_NONFINITE;
+    return status;
+}
+
 }  // namespace sfb

@@ -52,3 +52,14 @@ def test_c_caller_matches_python_binding(tmp_path):
     ug[:] = np.diag([0.5, 0.5, -1.0])
     y = sf.step_arr(x, ug, dt=0.01, terms=("lrot", "reg"), nsteps=5)
     assert np.array_equal(vals[:, 0] + 1j * vals[:, 1], y[0])
+
+
+@pytest.mark.gpu
+def test_c_caller_multi_device_entry_point(tmp_path):
+    """sfb_step_arr_multi from plain C over every device of the box: same bits as the one-device call."""
+    exe = build_c(tmp_path)
+    N = 1000
+    a = subprocess.run([exe, str(N)], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([exe, str(N), "multi"], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0, a.stdout + b.stdout + b.stderr
+    assert a.stdout == b.stdout and a.stdout.splitlines()[1] == "step 0"

@@ -443,3 +443,33 @@ def test_step_moments_Eij_on_reduced_form_states(n_grain):
     assert np.array_equal(f["Eij"].cpu().numpy(), r["Eij"].cpu().numpy()) and np.array_equal(f["a2"].cpu().numpy(), r["a2"].cpu().numpy())
     with pytest.raises(sf.SpecfabB200Error):
         sf.step_moments_Eij_rnlm_arr_dev(r["rnlm"], None, None, GRAIN, ALPHA, 3, step=False)
+
+
+def test_Evw_tranisotropic_parity():
+    """Evw_tranisotropic_arr (arbitrary v, w, tau per node) against the oracle's Evw_tranisotropic
+    (src/enhancementfactors.f90:47-69); the six eigenframe pairs of Eij_tranisotropic are the special case."""
+    import specfab_b200 as sf
+    sf.init(L)
+    orc.init(L)
+    N = 41
+    x = random_states(L, N, 81, True, decay=0.5)
+    rng = np.random.default_rng(82)
+    v = rng.standard_normal((N, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    w = rng.standard_normal((N, 3)); w /= np.linalg.norm(w, axis=1)[:, None]
+    tau = random_tau(N, 83)
+    for n_grain in (1, -3):
+        got = sf.Evw_tranisotropic_arr(x, v, w, tau, GRAIN, ALPHA, n_grain)
+        ref = np.array([orc.Evw_tranisotropic(v[p], w[p], tau[p], x[p], GRAIN, ALPHA, n_grain) for p in range(N)])
+        assert np.abs(got / ref - 1).max() < 1e-9
+    # Eij_tranisotropic = Evw with (e_i, e_j, tau_vv / tau_vw)   (src/enhancementfactors.f90:36-44, 398-413)
+    e = np.tile(np.eye(3)[None], (N, 1, 1))
+    E = sf.Eij_tranisotropic_arr(x, e[:, 0], e[:, 1], e[:, 2], GRAIN, ALPHA, 1)
+    tvv = np.eye(3)[None] / 3 - np.einsum("pi,pj->pij", e[:, 2], e[:, 2])
+    assert np.abs(sf.Evw_tranisotropic_arr(x, e[:, 2], e[:, 2], tvv, GRAIN, ALPHA, 1) / E[:, 2] - 1).max() < 1e-12
+    tvw = np.einsum("pi,pj->pij", e[:, 0], e[:, 2]) + np.einsum("pi,pj->pij", e[:, 2], e[:, 0])
+    assert np.abs(sf.Evw_tranisotropic_arr(x, e[:, 0], e[:, 2], tvw, GRAIN, ALPHA, 1) / E[:, 4] - 1).max() < 1e-12
+    assert abs(sf.Evw_tranisotropic(x[0], v[0], w[0], tau[0], GRAIN, ALPHA, 1) - orc.Evw_tranisotropic(v[0], w[0], tau[0], x[0], GRAIN, ALPHA, 1)) < 1e-9 * abs(got[0]) + 1e-9
+    with pytest.raises(sf.SpecfabB200Error):
+        sf.Evw_tranisotropic_arr(x, v, w, tau, GRAIN, ALPHA, 3)
+    with pytest.raises(ValueError):
+        sf.Evw_tranisotropic_arr(x, v[:-1], w, tau, GRAIN, ALPHA, 1)

@@ -361,3 +361,40 @@ def test_pin_array_in_place():
             sf.unpin_array(a)
     with pytest.raises(ValueError):
         sf.pin_array(np.zeros((4, 4))[::2])
+
+
+def test_multi_device_entry_point_and_general_flag():
+    """sfb_step_arr_multi (contiguous node ranges on 32-node boundaries, one host thread per device): bit-identical to the
+    one-device call for every device list the box offers; error paths; SFB_STEP_GENERAL."""
+    import specfab_b200 as sf
+    from specfab_b200 import _lib
+    L = 8
+    sf.init(L)
+    nd = _lib.load().sfb_device_count()
+    N = 5_003
+    x = random_states(L, N, 71, True)
+    ug, tau = random_ugrad(N, 72), random_tau(N, 73)
+    g0 = np.linspace(1.0, 4.0, N)
+    kw = dict(dt=3e-3, Gamma0=g0, terms=("lrot", "ddrx", "reg"), nsteps=3)
+    ref = sf.step_arr(x, ug, tau, **kw)
+    lists = [[0]] + ([[0, 1], [1, 0]] if nd >= 2 else []) + ([list(range(nd))] if nd > 2 else [])
+    for devs in lists:
+        got = sf.step_arr(x, ug, tau, devices=devs, **kw)
+        assert np.array_equal(got, ref), devs
+    idx = [l * (l + 1) // 2 + m for l in range(0, L + 1, 2) for m in range(0, l + 1)]
+    rgot = sf.step_rnlm_arr(sf.nlm_to_rnlm_arr(x), ug, tau, devices=lists[-1], **kw)
+    assert np.array_equal(rgot, ref[:, idx])
+    for bad in ([], [nd], [0, 0], [-1]):
+        with pytest.raises(sf.SpecfabB200Error):
+            sf.step_arr(x, ug, tau, devices=bad, **kw)
+    # the general path on physical states: same result to round-off, and independent of the batch composition
+    kw1 = dict(dt=3e-3, Gamma0=2.0, terms=("lrot", "ddrx", "reg"))
+    a = sf.step_arr(x, ug, tau, general=True, **kw1)
+    b = sf.step_arr(x, ug, tau, **kw1)
+    assert relerr_nodes(a, b).max() < 1e-13
+    sel = np.arange(0, N, 7)
+    assert np.array_equal(sf.step_arr(x[sel], ug[sel], tau[sel], general=True, **kw1), a[sel])
+    with pytest.raises(sf.SpecfabB200Error):
+        o = sf._opts(1e-3, 1.0, 0.0, 1.0, 0.0, 0.0, ("lrot",), "euler", 1)
+        o.reserved = 2
+        _lib.check(_lib.load().sfb_step_arr(x.ctypes.data, x.ctypes.data, 1, 1, ug.ctypes.data, None, __import__("ctypes").byref(o)))
