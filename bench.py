@@ -1,25 +1,32 @@
 #!/usr/bin/env python3
 """bench.py -- fabric node-updates/s of the B200 fabric-evolution engine (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--config 2|3|4|5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--config 2|3|4|5] [--scaling weak|strong --nodes-total T] [--impl reference]
 
-One "step" = one time step of every node of the synthetic field (SURVEY.md 8d inputs).  Default
-workload = BASELINE config 2 (configs[1]): Eulerian field of 1e6 nodes per GPU, L=8, LROT+REG,
-RK4, synthetic per-node velocity gradients.  N>1: one process per GPU (torchrun), contiguous node
-ranges, no collective while stepping (weak scaling: 1e6 nodes per GPU); the only NCCL traffic is
-the barrier and the max-over-ranks reduction of the device time.
+One "step" = one time step of every node of the synthetic field (SURVEY.md 8d inputs).  Default workload = BASELINE config 2
+(configs[1], the configuration the metric is quoted on that fits one GPU): Eulerian field of 1e6 nodes per GPU, L=8, LROT+REG,
+RK4, synthetic per-node velocity gradients, weak scaling.  N>1: one process per GPU (torchrun), contiguous node ranges
+(specfab_b200/shard.py), NO collective while stepping; the only NCCL traffic is the barrier and the max-over-ranks reduction
+of the device time.
 
-Prints ONE JSON line (rank 0).  `value` = node-updates/s with the state resident in HBM, timed
-with CUDA events on the launch stream; `e2e` = the same metric through the host-pointer C-ABI
-call (pinned host buffers, H2D + D2H inside the timed region); `roofline` for the step kernel
-(FP64 CUDA-core bound: peak = measured DFMA-chain peak, profiles/r01_fp64_peak.json; the HBM
-fraction against MEASURED_PEAKS.json is reported next to it); `cpu_baseline` = the dense C
-restatement of the reference algorithm (oracle/, gfortran is unavailable) on the host cores.
---impl reference runs that CPU restatement instead of the GPU engine.
+Prints ONE JSON line (rank 0):
+  value        node-updates/s, state resident in HBM, CUDA events on the launch stream, max over ranks
+  e2e          the same metric through the host-pointer C ABI (sfb_step_arr): pinned host buffers, H2D + D2H inside the timed
+               region every step; `pageable` = the same call on plain (unpinned) arrays, what an unmodified caller gets
+  roofline     FP64 CUDA-core bound: achieved = 2 flop x FP64-pipe slots per node-step x node rate against the DFMA-chain peak
+               measured live by tools/fp64_peak (NVML clocks recorded next to it); the HBM fraction is reported beside it
+  other_configs  at EVERY world size: BASELINE configs 3 and 5 on a 1e7-node field sharded over the ranks (strong scaling,
+               the curve north_star asks for), each with its own roofline block; at one GPU additionally config 4, the
+               stand-alone Eij rate, the reduced-form variants and the coupler-style end-to-end leg of config 5
+  parity_spot_max_rel   256 sampled nodes of the TIMED state against the CPU oracle replaying the same steps (outside the timed
+               region) -- the state the benchmark times is the state the parity tests vouch for
+  cpu_baseline the dense C restatement of the reference algorithm (oracle/; no Fortran compiler in the image) on the host cores
+--impl reference runs that CPU restatement instead of the GPU engine (same config dict).
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -27,23 +34,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import numpy as np
 
 DT = -np.log(0.02) / 1000          # strain -0.98 in 1000 steps (demo/fabric-evolution/...latrot.py:34)
+SEED = 20260817
 CONFIGS = {
-    # id: (L, nodes per GPU, terms, scheme, with Eij outputs, description)
+    # id: (L, nodes per GPU (weak default), terms, scheme, with Eij outputs, description)
     2: (8, 1_000_000, ("lrot", "reg"), "rk4", False, "cfg2: 1e6 nodes/GPU, L=8, LROT+REG, RK4, synthetic ugrad"),
-    3: (12, 1_250_000, ("lrot", "ddrx", "reg"), "euler", False, "cfg3: 1e7 nodes over 8 GPUs (1.25e6/GPU), L=12, LROT+DDRX+REG, Euler"),
+    3: (12, 1_250_000, ("lrot", "ddrx", "reg"), "euler", False, "cfg3: 1e7-node field, L=12, LROT+DDRX+REG, Euler, synthetic stress"),
     4: (20, 1_000_000, ("lrot", "ddrx", "cdrx", "reg"), "euler", False, "cfg4: 1e6 nodes/GPU, L=20, LROT+CDRX+DDRX+REG, Euler"),
-    5: (8, 1_250_000, ("lrot", "ddrx", "reg"), "euler", True, "cfg5: 1e7 nodes over 8 GPUs (1.25e6/GPU), L=8, step + a2/eig/Eij per node"),
+    5: (8, 1_250_000, ("lrot", "ddrx", "reg"), "euler", True, "cfg5: 1e7-node field, L=8, full step + a2/eigenframe/Eij per node"),
 }
 GRAIN, ALPHA = (1.0, 1e3), 0.0125   # ice 'linear' (src/specfabpy/constants.py:10)
+SPINUP = 50                          # Euler steps from isotropy so that every coefficient is non-zero
 
 
 def synth_forcing(N, seed):
-    """ugrad = traceless standard normal scaled to ||D||_F = sqrt(1.5); tau = traceless
-    symmetric normal scaled to ||tau||_F = 1.  Fortran (N,3,3) order = numpy (3,3,N)[k,i,p]."""
+    """SURVEY.md 8d (numpy, CPU arm): ugrad = traceless standard normal scaled to ||D||_F = sqrt(1.5); tau = traceless
+    symmetric normal scaled to ||tau||_F = 1.  (N,3,3)."""
     rng = np.random.default_rng(seed)
     u = rng.standard_normal((N, 3, 3))
     u -= np.eye(3)[None] * (np.trace(u, axis1=1, axis2=2) / 3)[:, None, None]
@@ -56,8 +66,27 @@ def synth_forcing(N, seed):
     return u, t
 
 
+def synth_forcing_dev(torch, N, seed):
+    """The same distributions generated on the device (1e7-node fields would take ~20 s of numpy): library layout (3,3,N),
+    element [k,i,p] = ugrad(p,i,k)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    u = torch.randn((3, 3, N), generator=g, dtype=torch.float64, device="cuda")
+    tr = (u[0, 0] + u[1, 1] + u[2, 2]) / 3
+    for i in range(3):
+        u[i, i] -= tr
+    D = (u + u.transpose(0, 1)) / 2
+    u *= (np.sqrt(1.5) / torch.sqrt((D * D).sum(dim=(0, 1))))
+    a = torch.randn((3, 3, N), generator=g, dtype=torch.float64, device="cuda")
+    t = (a + a.transpose(0, 1)) / 2
+    tr = (t[0, 0] + t[1, 1] + t[2, 2]) / 3
+    for i in range(3):
+        t[i, i] -= tr
+    t /= torch.sqrt((t * t).sum(dim=(0, 1)))
+    return u.contiguous(), t.contiguous()
+
+
 class ClockSampler(threading.Thread):
-    """samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)"""
+    """samples SM clock and throttle reasons of one GPU while a timed region runs (NVML)"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -97,35 +126,86 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def _cpus_of_node(node):
+    cpus = set()
+    for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa(torch, local):
     """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node of its GPU -- the
-    host-pointer leg moves 1.5 KB per node-step across PCIe and every rank does so at once.  Best effort: any failure (no
-    sysfs entry, cpuset without local cores) leaves the affinity alone.  Returns a short description for the JSON line."""
+    host-pointer leg moves 1.5 KB per node-step across PCIe and every rank does so at once.  sysfs first; where it reports -1
+    (the driver's box in round 1) the CPU-affinity column of `nvidia-smi topo -m`.  Best effort: any failure leaves the
+    affinity alone.  Returns a short description for the JSON line."""
     try:
         pr = torch.cuda.get_device_properties(local)
         bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
-        if node < 0:
-            return "numa node unknown"
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return "numa node %d has no allowed cpus" % node
-        os.sched_setaffinity(0, cpus)
-        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+        if node >= 0:
+            cpus = _cpus_of_node(node) & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return "bound to numa node %d (%d cpus, sysfs)" % (node, len(cpus))
+    except Exception:
+        pass
+    try:
+        phys = local
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            phys = int(vis.split(",")[local])
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        import re
+        out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+        hdr = None
+        for ln in out.splitlines():
+            cells = [c.strip() for c in ln.split("\t")]
+            if "CPU Affinity" in cells:
+                hdr = cells
+            elif hdr and cells and cells[0] == "GPU%d" % phys:
+                aff = cells[hdr.index("CPU Affinity")]
+                cpus = set()
+                for part in aff.split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                cpus &= os.sched_getaffinity(0)
+                if cpus and cpus != os.sched_getaffinity(0):
+                    os.sched_setaffinity(0, cpus)
+                    return "bound to cpus %s (nvidia-smi topo)" % aff
+                return "gpu-local cpus %s = all allowed cpus: nothing to bind" % aff
     except Exception as ex:   # noqa
         return "not bound (%s)" % type(ex).__name__
+    return "numa node unknown"
 
 
-def fp64_peak():
-    p = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+def stored_fp64_peak():
+    for nm in ("r02_fp64_peak.json", "r01_fp64_peak.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", nm)))["fp64_tflops_sustained"], "profiles/" + nm
+        except Exception:
+            pass
+    return 37.0, "nominal FP64 (fallback; no measured peak file)"
+
+
+def live_fp64_peak(local):
+    """run the DFMA-chain micro-benchmark (tools/fp64_peak.cu) on this GPU, outside any timed region, with NVML clock samples"""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    if not os.path.exists(exe):
+        return None
+    smp = ClockSampler(local)
+    smp.start()
     try:
-        return json.load(open(p))["fp64_tflops_sustained"], "measured DFMA-chain peak (profiles/r01_fp64_peak.json, tools/fp64_peak.cu)"
-    except Exception:
-        return 37.0, "nominal FP64 (fallback; profiles/r01_fp64_peak.json missing)"
+        env = dict(os.environ)
+        vis = env.get("CUDA_VISIBLE_DEVICES")
+        env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[local] if vis else str(local)
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        return {"burst_tflops": d["fp64_tflops_burst"], "sustained_tflops": d["fp64_tflops_sustained"], "clocks": smp.result(),
+                "how": "tools/fp64_peak: 8 independent DFMA chains per thread, best of 5 launches (burst) and 3 s back to back (sustained)"}
+    except Exception as ex:   # noqa
+        smp.result()
+        return {"error": str(ex)[:120]}
 
 
 def hbm_peak():
@@ -142,18 +222,73 @@ def alg_bytes_per_node_step(n, terms, eij):
     return b
 
 
+def config_dict(cfg, n, N_local, world, scaling, total):
+    L, _, terms, scheme, eij, desc = CONFIGS[cfg]
+    return {"workload": desc, "L": L, "nlm_len": n, "nodes_per_gpu": N_local, "nodes_total": total, "terms": "+".join(terms),
+            "scheme": scheme, "dt": DT, "scaling": scaling,
+            "l2": "inputs exceed L2 (state %.0f MB per GPU vs 126 MB L2); no flush needed" % (N_local * n * 16 / 1e6),
+            "sharding": "contiguous node ranges, no collective while stepping"}
+
+
+def measured_ops():
+    """profiles/fp64_ops.json (executed FP64 instructions per node-step, ncu) -- only when it was captured on THIS source tree"""
+    try:
+        import stamp
+        d = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json")))
+        if d.get("_stamp") == stamp.tree_hash():
+            return d, "profiles/fp64_ops.json (stamp %s matches the source tree)" % d["_stamp"]
+        return None, "codegen count only: profiles/fp64_ops.json is stale (stamp %s, tree %s)" % (d.get("_stamp"), stamp.tree_hash())
+    except Exception as ex:   # noqa
+        return None, "codegen count only (%s)" % type(ex).__name__
+
+
+def roofline_block(sf, key, L, terms, scheme, eij, n, ms_step, N_local, fpk, fsrc, hpk, hsrc, ops_db, ops_src, traffic_db):
+    """FP64 work per node-step in FP64-pipe instruction slots (a DFMA, DMUL or DADD occupies the pipe alike; the measured peak
+    is a DFMA chain = 2 flop per slot), counted conservatively: min(instructions the kernel EXECUTES per ncu, the code
+    generator's count of the factorised algorithm, which excludes the zero padding the table-driven loop kernels execute)."""
+    info = [k for k in sf.build_info()["step_kernels"] if k["L"] == L and k["ddrx"] == int("ddrx" in terms) and k["variant"] == 0][0]
+    nst = 4 if scheme == "rk4" else 1
+    nominal = info["dfma_per_node_rhs"] * nst
+    ops = ops_db.get(key) if ops_db else None
+    executed = (ops["dfma"] + ops["dmul"] + ops["dadd"]) if ops else None
+    slots = min(executed, nominal) if executed else nominal
+    rate = N_local / (ms_step * 1e-3)
+    ach_tf = 2.0 * slots * rate / 1e12
+    ab = alg_bytes_per_node_step(n, terms, False)
+    ach_gb = ab * rate / 1e9
+    fp_frac, hbm_frac = ach_tf / fpk, ach_gb / hpk
+    if fp_frac >= hbm_frac:
+        roof = {"bound": "fp64", "achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc}
+    else:
+        roof = {"bound": "hbm", "achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc}
+    roof.update({"traffic": (traffic_db or {}).get(key),
+                 "kernel": "fused step kernel, L=%d, %s, %s (registry variant %s: %d role(s), %d-node tiles)"
+                           % (L, "+".join(terms), scheme, "100/0" if nst > 1 else "0", info["roles"], info["tile"]),
+                 "fp64_slots_per_node_step": slots, "fp64_slots_codegen_per_node_step": nominal,
+                 "fp64_ops_executed_per_node_step": ({"dfma": ops["dfma"], "dmul": ops["dmul"], "dadd": ops["dadd"]} if ops else None),
+                 "ncu_pipe_fp64_pct": (ops or {}).get("pipe_fp64_pct"), "ops_source": ops_src,
+                 "alg_bytes_per_node_step": ab,
+                 "hbm": {"achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc},
+                 "fp64": {"achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc}})
+    return roof
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arm: dense C restatement of the reference algorithm (oracle/specfab_oracle.c)
 # ----------------------------------------------------------------------------------------------
+def oracle_kw(terms, scheme):
+    return dict(dt=DT, Gamma0=4.0, Lambda=1.0, use_lrot="lrot" in terms, use_ddrx="ddrx" in terms, use_cdrx="cdrx" in terms,
+                use_reg="reg" in terms, scheme=scheme)
+
+
 def cpu_rate(cfg, nodes, reps=1):
     import oracle_c as oc
     L, _, terms, scheme, eij, _ = CONFIGS[cfg]
     n = oc.init(L)
-    u, t = synth_forcing(nodes, 20260817)
+    u, t = synth_forcing(nodes, SEED)
     x = np.zeros((nodes, n), dtype=np.complex128)
     x[:, 0] = 1 / np.sqrt(4 * np.pi)
-    kw = dict(dt=DT, Gamma0=4.0, Lambda=1.0, use_lrot="lrot" in terms, use_ddrx="ddrx" in terms, use_cdrx="cdrx" in terms,
-              use_reg="reg" in terms, scheme=scheme)
+    kw = oracle_kw(terms, scheme)
     x = oc.step_batch(x, u, t, nsteps=2, **kw)     # leave isotropy so that all coefficients are non-zero
     best = 0.0
     for _ in range(reps):
@@ -166,19 +301,27 @@ def cpu_rate(cfg, nodes, reps=1):
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm on the host cores (C port: no Fortran compiler)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cfg = args.config
     L, npg, terms, scheme, eij, desc = CONFIGS[cfg]
+    from specfab_b200.shard import node_range
+    if args.scaling == "strong":
+        total = args.nodes_total or 10_000_000
+        lo, hi = node_range(total, 0, world)
+        N_local = hi - lo
+    else:
+        N_local = args.nodes or npg
+        total = N_local * world
     probe, cores = cpu_rate(cfg, 2000)
-    sample = int(max(2000, min(npg, probe * 2.0)))           # ~2 s of CPU work per step
+    sample = int(max(2000, min(N_local, probe * 2.0)))           # ~2 s of CPU work per step
     import oracle_c as oc
     n = oc.init(L)
-    u, t = synth_forcing(sample, 20260817)
+    u, t = synth_forcing(sample, SEED)
     x = np.zeros((sample, n), dtype=np.complex128)
     x[:, 0] = 1 / np.sqrt(4 * np.pi)
-    kw = dict(dt=DT, Gamma0=4.0, Lambda=1.0, use_lrot="lrot" in terms, use_ddrx="ddrx" in terms, use_cdrx="cdrx" in terms,
-              use_reg="reg" in terms, scheme=scheme)
+    kw = oracle_kw(terms, scheme)
     for _ in range(args.warmup):
         x = oc.step_batch(x, u, t, nsteps=1, **kw)
     t0 = time.perf_counter()
@@ -188,11 +331,11 @@ def run_reference(args):
     val = sample * args.steps / el
     line = {"impl": "reference", "metric": "fabric node-updates/s", "value": val, "unit": "node-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "L": L, "terms": "+".join(terms), "scheme": scheme},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(cfg, n, N_local, world, args.scaling, total),
             "cpu_baseline": {"value": val, "unit": "node-updates/s", "cores": cores, "kind": "port",
-                             "sample": "%d nodes per step (bounded sample of the workload); dense per-node operator build + matvec, "
-                                       "C restatement of src/dynamics.f90:94-96,108 (no Fortran compiler in the image)" % sample},
+                             "sample": "%d nodes per step (bounded sample of the workload; a rate, so comparable); dense per-node operator "
+                                       "build + matvec, C restatement of src/dynamics.f90:94-96,108 (no Fortran compiler in the image)" % sample},
             "e2e": {"value": val, "unit": "node-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -206,20 +349,20 @@ def rnlm_rows(L):
     return [lm.index((l, m)) for l in range(0, L + 1, 2) for m in range(0, l + 1)]
 
 
-def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None, reduced=False, scheme=None):
-    """device-resident timing of one config; returns (ms_per_step_local, launches_per_step, n).
-    reduced=True: the state is kept in reduced form (rnlm) and stepped with step_rnlm_arr_dev."""
+def time_config(sf, torch, cfg, N, seed, steps, warmup, sampler=None, reduced=False, scheme=None, spot=0, sync=None):
+    """Device-resident timing of one config on this rank's N nodes.  Returns a dict: ms (all launches of a step), ms_step
+    (the fused step kernel alone, timed in a second loop when the config also evaluates Eij), n, finite, launches per step,
+    spot (max relative error of `spot` sampled nodes of the TIMED state against the CPU oracle replaying the same steps)."""
     L, _, terms, scheme0, eij, _ = CONFIGS[cfg]
     scheme = scheme or scheme0
     lm, n = sf.init(L)
-    u, t = synth_forcing(N, 20260817 + rank)
-    ug = torch.from_numpy(np.ascontiguousarray(u.transpose(2, 1, 0))).cuda()     # (3,3,N): [k,i,p]
-    tau = torch.from_numpy(np.ascontiguousarray(t.transpose(2, 1, 0))).cuda() if "ddrx" in terms else None
+    ug, tau = synth_forcing_dev(torch, N, seed)
+    if "ddrx" not in terms:
+        tau = None
     nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
     nlm[0] = 1 / np.sqrt(4 * np.pi)
     kw = dict(dt=DT, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
-    # 50 spin-up steps from isotropy so that every coefficient is non-zero (SURVEY.md 8d)
-    for _ in range(50):
+    for _ in range(SPINUP):
         sf.step_arr_dev(nlm, ug, tau, dt=DT, Gamma0=4.0, Lambda=1.0, terms=terms, scheme="euler")
     stepf = sf.step_arr_dev
     if reduced:
@@ -230,13 +373,15 @@ def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None, reduced=Fa
     eiv = torch.empty((3, 3, N), dtype=torch.float64, device="cuda") if eij else None
     lam = torch.empty((3, N), dtype=torch.float64, device="cuda") if eij else None
 
-    def one():
+    def one(with_eij=True):
         stepf(nlm, ug, tau, **kw)
-        if eij:
+        if eij and with_eij:
             sf.Eij_eigenframe_arr_dev(nlm, GRAIN, ALPHA, 1, out=eout, ei=eiv, lami=lam)
 
     for _ in range(warmup):
         one()
+    if sync:
+        sync()
     torch.cuda.synchronize()
     if sampler:
         sampler.start()
@@ -247,40 +392,73 @@ def time_config(sf, torch, cfg, N, rank, steps, warmup, sampler=None, reduced=Fa
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    nsteps_done = warmup + steps
+    ms_step = ms
+    if eij:      # the fused step kernel alone (its roofline), same state
+        e0.record()
+        for _ in range(steps):
+            one(False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / steps
+        nsteps_done += steps
     finite = bool(torch.isfinite(torch.view_as_real(nlm)).all().item())
+    spot_err = None
+    if spot and not reduced:
+        try:
+            import oracle_c as oc
+            oc.init(L)
+            idx = torch.from_numpy(np.random.default_rng(1).choice(N, min(spot, N), replace=False)).cuda()
+            u_h = ug[:, :, idx].cpu().numpy().transpose(2, 1, 0).copy()                 # (S,3,3): ugrad(p,i,k)
+            t_h = tau[:, :, idx].cpu().numpy().transpose(2, 1, 0).copy() if tau is not None else None
+            x = np.zeros((len(idx), n), dtype=np.complex128)
+            x[:, 0] = 1 / np.sqrt(4 * np.pi)
+            x = oc.step_batch(x, u_h, t_h, nsteps=SPINUP, **oracle_kw(terms, "euler"))
+            x = oc.step_batch(x, u_h, t_h, nsteps=nsteps_done, **oracle_kw(terms, scheme))
+            got = nlm[:, idx].cpu().numpy().T
+            spot_err = float((np.abs(got - x).max(axis=1) / np.abs(x).max(axis=1)).max())
+        except Exception as ex:   # noqa
+            spot_err = "failed: %s" % str(ex)[:100]
     del nlm, ug, tau, eout, eiv, lam
     torch.cuda.empty_cache()
-    return ms, (2 if eij else 1), n, finite
+    return {"ms": ms, "ms_step": ms_step, "n": n, "finite": finite, "launches": 2 if eij else 1, "spot": spot_err,
+            "spot_steps": "%d Euler spin-up + %d %s steps" % (SPINUP, nsteps_done, scheme)}
 
 
-def time_e2e(sf, torch, cfg, N, rank, steps, warmup, reduced=False):
-    """the same step through the host-pointer C-ABI call: pinned host buffers, H2D of state + forcing and
-    D2H of the new state inside the timed region, every step.  reduced=True: sfb_step_rnlm_arr on reduced-form states."""
+def pinned(torch, shape, dtype):
+    return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+
+def time_e2e(sf, torch, cfg, N, seed, steps, warmup, reduced=False, pageable=False):
+    """The same step through the host-pointer C-ABI call: host buffers (pinned, or plain pageable numpy arrays), H2D of state +
+    forcing and D2H of the new state inside the timed region, every step.  reduced=True: sfb_step_rnlm_arr."""
     L, _, terms, scheme, eij, _ = CONFIGS[cfg]
     lm, n = sf.init(L)
     hstep = sf.step_arr
     if reduced:
         n = sf.rnlm_len()
         hstep = sf.step_rnlm_arr
-    u, t = synth_forcing(N, 20260817 + rank)
+    u, t = synth_forcing(N, seed)
 
-    def pinned(shape, dtype):
-        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+    def host(shape, dtype):
+        if pageable:
+            return np.empty(shape, dtype=np.complex128 if dtype == torch.complex128 else np.float64)
+        return pinned(torch, shape, dtype)
 
-    x = pinned((n, N), torch.complex128).T        # Fortran-ordered (N, n) view of pinned memory
+    x = host((n, N), torch.complex128).T        # Fortran-ordered (N, n) view
     x[:] = 0
     x[:, 0] = 1 / np.sqrt(4 * np.pi)
-    ugp = pinned((3, 3, N), torch.float64).transpose(2, 1, 0)
+    ugp = host((3, 3, N), torch.float64).transpose(2, 1, 0)
     ugp[:] = u
     tp = None
     if "ddrx" in terms:
-        tp = pinned((3, 3, N), torch.float64).transpose(2, 1, 0)
+        tp = host((3, 3, N), torch.float64).transpose(2, 1, 0)
         tp[:] = t
     kw = dict(dt=DT, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
     x = hstep(x, ugp, tp, **dict(kw, scheme="euler", nsteps=20))
-    xin = pinned((n, N), torch.complex128).T
+    xin = host((n, N), torch.complex128).T
     xin[:] = x
-    xout = pinned((n, N), torch.complex128).T
+    xout = host((n, N), torch.complex128).T
     for _ in range(warmup):
         hstep(xin, ugp, tp, out=xout, **kw)
     t0 = time.perf_counter()
@@ -294,6 +472,48 @@ def time_e2e(sf, torch, cfg, N, rank, steps, warmup, reduced=False):
     return el / steps, h2d, d2h
 
 
+def time_coupler(sf, torch, N, seed, steps, warmup):
+    """BASELINE config 5 the way an FE coupler drives it: the state stays resident on the device; per time step the new
+    velocity gradients and stresses come in from pinned host memory (144 B per node) and Eij, the eigenframe and the
+    eigenvalues go back (144 B per node).  One stream: H2D -> fused step -> a2/eigenframe/Eij -> D2H, timed on the host."""
+    L, _, terms, scheme, _, _ = CONFIGS[5]
+    lm, n = sf.init(L)
+    u, t = synth_forcing(N, seed)
+    hu = torch.from_numpy(np.ascontiguousarray(u.transpose(2, 1, 0))).pin_memory()
+    ht = torch.from_numpy(np.ascontiguousarray(t.transpose(2, 1, 0))).pin_memory()
+    du, dtau = torch.empty_like(hu, device="cuda"), torch.empty_like(ht, device="cuda")
+    nlm = torch.zeros((n, N), dtype=torch.complex128, device="cuda")
+    nlm[0] = 1 / np.sqrt(4 * np.pi)
+    dE = torch.empty((6, N), dtype=torch.float64, device="cuda")
+    dei = torch.empty((3, 3, N), dtype=torch.float64, device="cuda")
+    dlam = torch.empty((3, N), dtype=torch.float64, device="cuda")
+    hE, hei, hlam = (torch.empty(x.shape, dtype=torch.float64).pin_memory() for x in (dE, dei, dlam))
+    kw = dict(dt=DT, Gamma0=4.0, Lambda=1.0, terms=terms, scheme=scheme)
+
+    def one():
+        du.copy_(hu, non_blocking=True)
+        dtau.copy_(ht, non_blocking=True)
+        sf.step_arr_dev(nlm, du, dtau, **kw)
+        sf.Eij_eigenframe_arr_dev(nlm, GRAIN, ALPHA, 1, out=dE, ei=dei, lami=dlam)
+        hE.copy_(dE, non_blocking=True)
+        hei.copy_(dei, non_blocking=True)
+        hlam.copy_(dlam, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(SPINUP):
+        sf.step_arr_dev(nlm, du.copy_(hu), dtau.copy_(ht), **kw)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    el = (time.perf_counter() - t0) / steps
+    ok = bool(np.isfinite(hE.numpy()).all())
+    del nlm, du, dtau, dE, dei, dlam
+    torch.cuda.empty_cache()
+    return el, 144 * N, 144 * N, ok
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,7 +521,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
-    ap.add_argument("--nodes", type=int, default=None, help="nodes per GPU (default: the config's)")
+    ap.add_argument("--nodes", type=int, default=None, help="nodes per GPU (weak scaling; default: the config's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--nodes-total", type=int, default=None, help="field size for --scaling strong (default 1e7)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs / cpu baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -311,6 +533,7 @@ def main():
     import torch
     import torch.distributed as dist
     import specfab_b200 as sf
+    from specfab_b200.shard import node_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,139 +560,147 @@ def main():
 
     cfg = args.config
     L, npg, terms, scheme, eij, desc = CONFIGS[cfg]
-    N = args.nodes or npg
+    if args.scaling == "strong":
+        total = args.nodes_total or 10_000_000
+        lo, hi = node_range(total, rank, world)
+        N = hi - lo
+    else:
+        N = args.nodes or npg
+        total = N * world
+
+    # ---- peaks (outside every timed region)
+    hpk, hsrc = hbm_peak()
+    fpk, fsrc = stored_fp64_peak()
+    live = None
+    if rank == 0 and not args.no_extra:
+        live = live_fp64_peak(local)
+        if live and live.get("burst_tflops"):
+            fpk, fsrc = live["burst_tflops"], "DFMA-chain peak measured in this run (tools/fp64_peak; kernel timed alone: burst figure)"
+    if world > 1:
+        t_ = torch.tensor([fpk], dtype=torch.float64, device="cuda")
+        dist.broadcast(t_, 0)
+        fpk = float(t_.item())
+    ops_db, ops_src = measured_ops()
+    traffic_db = None
+    try:
+        import stamp
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic_db = tr if tr.get("_stamp") == stamp.tree_hash() else None
+    except Exception:
+        pass
+
+    # ---- headline: device-resident
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    ms, lps, n, finite = time_config(sf, torch, cfg, N, rank, args.steps, args.warmup, sampler)
+    r = time_config(sf, torch, cfg, N, SEED + rank, args.steps, args.warmup, sampler, spot=256 if rank == 0 else 0, sync=barrier)
     clocks = sampler.result() if sampler else None
     barrier()
-    ms = max_over_ranks(ms)
-    value = N * world / (ms * 1e-3)
+    ms = max_over_ranks(r["ms"])
+    ms_step = max_over_ranks(r["ms_step"])
+    n = r["n"]
+    value = total / (ms * 1e-3)
 
-    # end-to-end through the host-pointer C ABI (fewer steps: PCIe bound)
+    # ---- end to end through the host-pointer C ABI (fewer steps: PCIe bound)
     e2e_steps = max(2, min(args.steps, 5))
     barrier()
-    sec, h2d, d2h = time_e2e(sf, torch, cfg, N, rank, e2e_steps, 1)
+    sec, h2d, d2h = time_e2e(sf, torch, cfg, N, SEED + rank, e2e_steps, 1)
     barrier()
     sec = max_over_ranks(sec)
-    e2e_val = N * world / sec
+    e2e_val = total / sec
+    e2e = {"value": e2e_val, "unit": "node-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "api": "sfb_step_arr (host pointers, pinned buffers, chunked H2D|kernel|D2H pipeline)", "host_affinity": numa}
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            secp, _, _ = time_e2e(sf, torch, cfg, N, SEED + rank, 2, 1, pageable=True)
+            e2e["pageable"] = {"value": N / secp, "unit": "node-updates/s",
+                               "what": "the same call on plain numpy (pageable) arrays: what a caller gets without pinning or sfb_host_register"}
+        except Exception as ex:   # noqa
+            e2e["pageable"] = {"error": str(ex)[:160]}
 
-    info = [k for k in sf.build_info()["step_kernels"] if k["L"] == L and k["ddrx"] == int("ddrx" in terms) and k["variant"] == 0][0]
-    nst = 4 if scheme == "rk4" else 1
-    per_gpu_rate = N / (ms * 1e-3)
-    fpk, fsrc = fp64_peak()
-    hpk, hsrc = hbm_peak()
-    # FP64 work per node-step, in FP64-pipe instruction slots (a DFMA, DMUL or DADD occupies the pipe alike; the measured
-    # peak is a DFMA chain = 2 flop per slot).  Counted conservatively: min(instructions the kernel EXECUTES -- ncu,
-    # profiles/fp64_ops.json; the compiler drops e.g. the imaginary parts of the m = 0 rows --, the code generator's count
-    # of the factorised algorithm -- which excludes the zero padding the table-driven loop kernels execute).
-    nominal = info["dfma_per_node_rhs"] * nst
-    ops = None
-    try:
-        ops = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json"))).get({2: "cfg2", 3: "cfg3", 4: "cfg4", 5: "cfg5_step"}[cfg])
-    except Exception:
-        pass
-    executed = (ops["dfma"] + ops["dmul"] + ops["dadd"]) if ops else None
-    slots = min(executed, nominal) if executed else nominal
-    ach_tf = 2.0 * slots * per_gpu_rate / 1e12
-    ach_gb = alg_bytes_per_node_step(n, terms, eij) * per_gpu_rate / 1e9
-    fp_frac, hbm_frac = ach_tf / fpk, ach_gb / hpk
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get("cfg%d" % cfg)
-    except Exception:
-        pass
-    if fp_frac >= hbm_frac:
-        roof = {"bound": "fp64", "achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc}
-    else:
-        roof = {"bound": "hbm", "achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc}
-    reduced = info["roles"] >= 1 and info["tile"] == 32 and any(
-        k["L"] == L and k["ddrx"] == info["ddrx"] and k["variant"] == 40 for k in sf.build_info()["step_kernels"])
-    roof.update({"traffic": traffic,
-                 "kernel": "%s (L=%d, %s, %s)" % ("step_kernel_r" if reduced else "step_kernel", L, "+".join(terms), scheme),
-                 "form": ("reduced: only the rows m >= 0 are computed (real-ODF symmetry of every 32-node tile verified in the kernel, "
-                          "full-form fallback otherwise; SURVEY.md 8d: flop counts scaled accordingly)") if reduced else "full",
-                 "fp64_accounting": "achieved = 2 flop x FP64-pipe instruction slots per node-step x node rate (DFMA-equivalent: DFMA, DMUL and "
-                                    "DADD occupy the pipe alike and the measured peak is a DFMA chain); slots = min(executed per ncu, "
-                                    "code generator's count); cross-check: ncu sm__pipe_fp64_cycles_active of the same kernel = "
-                                    "%s %% (profiles/fp64_ops.json)" % (ops["pipe_fp64_pct"] if ops else "n/a"),
-                 "fp64_slots_per_node_step": slots,
-                 "fp64_ops_executed_per_node_step": ({"dfma": ops["dfma"], "dmul": ops["dmul"], "dadd": ops["dadd"]} if ops else None),
-                 "flops_executed_per_node_step": (2 * ops["dfma"] + ops["dmul"] + ops["dadd"]) if ops else None,
-                 "fp64_slots_codegen_per_node_step": nominal,
-                 "alg_bytes_per_node_step": alg_bytes_per_node_step(n, terms, eij),
-                 "hbm": {"achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc},
-                 "fp64": {"achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc},
-                 "note": "FP64 CUDA-core (DFMA) bound path: tensor cores do not apply (DESIGN.md); the governing bound is reported"})
+    roof = roofline_block(sf, {2: "cfg2", 3: "cfg3", 4: "cfg4", 5: "cfg5_step"}[cfg], L, terms, scheme, eij, n, ms_step, N, fpk, fsrc,
+                          hpk, hsrc, ops_db, ops_src, traffic_db)
+    roof["fp64_peak_live"] = live
+    roof["fp64_peak_stored"] = dict(zip(("tflops", "source"), stored_fp64_peak()))
+    roof["tensor_cores"] = ("measured, not assumed: DMMA.8x8x4 peak 37.1 TFLOP/s vs DFMA 34.2 on this part and no overlap when both are "
+                            "issued (profiles/r02_dmma_peak.json); the dense K.n^2 contraction needs 3-18x the slots of the factorised "
+                            "sparse form, so CUDA-core FP64 governs (DESIGN.md 5.4)")
 
+    # ---- the 1e7-node field of BASELINE configs 3 and 5, sharded over the ranks (strong scaling), at every world size
     extra = {}
+    if not args.no_extra:
+        for c in (5, 3):
+            if c == cfg and args.scaling == "strong":
+                continue
+            try:
+                Lc, _, tc, sc, ec, dc = CONFIGS[c]
+                tot_c = 10_000_000
+                lo, hi = node_range(tot_c, rank, world)
+                barrier()
+                rc = time_config(sf, torch, c, hi - lo, SEED + 100 * c + rank, 10, 3, spot=64 if rank == 0 else 0, sync=barrier)
+                barrier()
+                m_all, m_step = max_over_ranks(rc["ms"]), max_over_ranks(rc["ms_step"])
+                ent = {"workload": dc, "scaling": "strong", "nodes_total": tot_c, "nodes_per_gpu": hi - lo, "ms_per_step": m_all,
+                       "node_updates_per_s": tot_c / (m_all * 1e-3), "finite": rc["finite"], "parity_spot_max_rel": rc["spot"],
+                       "roofline": roofline_block(sf, {3: "cfg3", 5: "cfg5_step"}[c], Lc, tc, sc, ec, rc["n"], m_step, hi - lo, fpk, fsrc,
+                                                  hpk, hsrc, ops_db, ops_src, traffic_db)}
+                if ec:
+                    ent["ms_step_kernel"] = m_step
+                    ent["eij_evals_per_s"] = tot_c / ((m_all - m_step) * 1e-3) if m_all > m_step else None
+                    ent["what"] = "node_updates_per_s counts the whole FE step (fused step + a2/eigenframe/Eij); roofline is the step kernel's"
+                extra["cfg%d_1e7" % c] = ent
+            except Exception as ex:   # noqa
+                extra["cfg%d_1e7" % c] = {"error": str(ex)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_extra:
+        # config 4 (L = 20) and the other weak-scaling shapes
         for c in sorted(CONFIGS):
-            if c == cfg:
+            if c == cfg or c in (3, 5):
                 continue
             try:
                 Lc, npc, tc, sc, ec, dc = CONFIGS[c]
-                Nc = min(npc, 1_000_000 if Lc >= 12 else npc)
-                m2, l2, n2, fin2 = time_config(sf, torch, c, Nc, rank, 10, 3)
-                extra["cfg%d" % c] = {"workload": dc, "nodes": Nc, "ms_per_step": m2, "node_updates_per_s": Nc / (m2 * 1e-3),
-                                      "finite": fin2}
+                rc = time_config(sf, torch, c, npc, SEED, 10, 3, spot=32)
+                extra["cfg%d" % c] = {"workload": dc, "nodes": npc, "ms_per_step": rc["ms"], "node_updates_per_s": npc / (rc["ms"] * 1e-3),
+                                      "finite": rc["finite"], "parity_spot_max_rel": rc["spot"],
+                                      "roofline": roofline_block(sf, "cfg%d" % c, Lc, tc, sc, ec, rc["n"], rc["ms_step"], npc, fpk, fsrc, hpk, hsrc,
+                                                                 ops_db, ops_src, traffic_db)}
             except Exception as ex:   # noqa
                 extra["cfg%d" % c] = {"error": str(ex)[:200]}
         # the headline workload on reduced-form states (rows m >= 0 only; the FE couplers' state representation)
         try:
-            r = (L + 2) ** 2 // 4
+            rl = (L + 2) ** 2 // 4
             rr = {}
+            slots_rhs = roof["fp64_slots_per_node_step"] / (4 if scheme == "rk4" else 1)
             for sc in ("rk4", "euler"):
-                m3, _, _, fin3 = time_config(sf, torch, cfg, N, rank, 10, 3, reduced=True, scheme=sc)
-                rr[sc] = {"ms_per_step": m3, "node_updates_per_s": N / (m3 * 1e-3), "alg_bytes_per_node_step": 32 * r + 72,
-                          "hbm_gbs_alg": (32 * r + 72) * N / (m3 * 1e-3) / 1e9, "hbm_frac": (32 * r + 72) * N / (m3 * 1e-3) / 1e9 / hpk,
-                          "fp64_frac": 2.0 * (slots / nst) * (4 if sc == "rk4" else 1) * N / (m3 * 1e-3) / 1e12 / fpk, "finite": fin3}
+                r3 = time_config(sf, torch, cfg, N, SEED, 10, 3, reduced=True, scheme=sc)
+                rate3 = N / (r3["ms_step"] * 1e-3)
+                rr[sc] = {"ms_per_step": r3["ms_step"], "node_updates_per_s": rate3, "alg_bytes_per_node_step": 32 * rl + 72,
+                          "hbm_frac": (32 * rl + 72) * rate3 / 1e9 / hpk,
+                          "fp64_frac": 2.0 * slots_rhs * (4 if sc == "rk4" else 1) * rate3 / 1e12 / fpk, "finite": r3["finite"]}
             if not eij:
-                sec3, h3, d3 = time_e2e(sf, torch, cfg, N, rank, 3, 1, reduced=True)
+                sec3, h3, d3 = time_e2e(sf, torch, cfg, N, SEED, 3, 1, reduced=True)
                 rr["e2e"] = {"value": N / sec3, "unit": "node-updates/s", "h2d_bytes_per_step": h3, "d2h_bytes_per_step": d3,
                              "api": "sfb_step_rnlm_arr (host pointers)"}
-            rr["workload"] = "%s, state in reduced form (rnlm: %d of %d coefficient rows), sfb_step_rnlm_arr(_dev)" % (desc, r, n)
+            rr["workload"] = "%s, state in reduced form (rnlm: %d of %d coefficient rows), sfb_step_rnlm_arr(_dev)" % (desc, rl, n)
             extra["rnlm"] = rr
         except Exception as ex:   # noqa
             extra["rnlm"] = {"error": str(ex)[:200]}
-        # BASELINE config 5 (FE coupling: step + eigenframe + Eij per node) on a field kept in reduced form
+        # config 5 the way an FE coupler drives it (state resident, forcing in, Eij + frame out)
         try:
-            L5, n5, t5, s5, _, d5 = CONFIGS[5]
-            sf.init(L5)
-            u5, tt5 = synth_forcing(n5, 20260817 + rank)
-            ug5 = torch.from_numpy(np.ascontiguousarray(u5.transpose(2, 1, 0))).cuda()
-            ta5 = torch.from_numpy(np.ascontiguousarray(tt5.transpose(2, 1, 0))).cuda()
-            st5 = torch.zeros((sf.rnlm_len(), n5), dtype=torch.complex128, device="cuda")
-            st5[0] = 1 / np.sqrt(4 * np.pi)
-            kw5 = dict(dt=DT, Gamma0=4.0, Lambda=1.0, terms=t5, scheme=s5)
-            for _ in range(50):
-                sf.step_rnlm_arr_dev(st5, ug5, ta5, **kw5)
-            for _ in range(3):
-                sf.step_moments_Eij_rnlm_arr_dev(st5, ug5, ta5, GRAIN, ALPHA, 1, want_frame=True, **kw5)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(10):
-                sf.step_moments_Eij_rnlm_arr_dev(st5, ug5, ta5, GRAIN, ALPHA, 1, want_frame=True, **kw5)
-            b.record()
-            torch.cuda.synchronize()
-            m5 = a.elapsed_time(b) / 10
-            extra["cfg5_rnlm"] = {"workload": d5 + ", state in reduced form (sfb_step_moments_Eij_rnlm_arr_dev)", "nodes": n5, "ms_per_step": m5,
-                                  "node_updates_per_s": n5 / (m5 * 1e-3), "finite": bool(torch.isfinite(torch.view_as_real(st5)).all().item())}
-            del st5, ug5, ta5
-            sf.init(L)
+            secc, hc, dc_, okc = time_coupler(sf, torch, 1_250_000, SEED, 5, 2)
+            extra["cfg5_coupler_e2e"] = {"value": 1_250_000 / secc, "unit": "node-updates/s", "h2d_bytes_per_step": hc, "d2h_bytes_per_step": dc_,
+                                         "nodes": 1_250_000, "finite": okc,
+                                         "what": "state resident in HBM; per step ugrad + tau in (144 B/node, pinned), Eij + eigenframe + "
+                                                 "eigenvalues out (144 B/node); sfb_step_arr_dev + sfb_Eij_eigenframe_arr_dev on one stream"}
         except Exception as ex:   # noqa
-            extra["cfg5_rnlm"] = {"error": str(ex)[:200]}
+            extra["cfg5_coupler_e2e"] = {"error": str(ex)[:200]}
         # stand-alone Eij evals/s (a2 -> eigenframe -> 6 Sachs/Taylor factors per node)
         try:
             lm, n8 = sf.init(8)
             Ne = 4_000_000
             st = torch.zeros((n8, Ne), dtype=torch.complex128, device="cuda")
             st[0] = 1 / np.sqrt(4 * np.pi)
-            ugq, _ = synth_forcing(Ne, 7)
-            ugd = torch.from_numpy(np.ascontiguousarray(ugq.transpose(2, 1, 0))).cuda()
+            ugd, _ = synth_forcing_dev(torch, Ne, 7)
             for _ in range(60):
                 sf.step_arr_dev(st, ugd, None, dt=DT, terms=("lrot", "reg"))
             eo = torch.empty((6, Ne), dtype=torch.float64, device="cuda")
@@ -483,14 +714,16 @@ def main():
             b.record()
             torch.cuda.synchronize()
             me = a.elapsed_time(b) / 10
-            extra["eij"] = {"workload": "stand-alone a2 -> eigenframe -> Eij_tranisotropic, 4e6 nodes, L=8", "ms": me,
-                            "eij_evals_per_s": Ne / (me * 1e-3), "hbm_gbs_alg": 288 * Ne / (me * 1e-3) / 1e9}
-            try:
-                eo_ = json.load(open(os.path.join(ROOT, "profiles", "fp64_ops.json")))["eij"]
-                sl = eo_["dfma"] + eo_["dmul"] + eo_["dadd"]
-                extra["eij"].update({"fp64_slots_per_eval": sl, "fp64_frac": 2.0 * sl * Ne / (me * 1e-3) / 1e12 / fpk})
-            except Exception:
-                pass
+            ent = {"workload": "stand-alone a2 -> eigenframe -> Eij_tranisotropic, 4e6 nodes, L=8", "ms": me,
+                   "eij_evals_per_s": Ne / (me * 1e-3)}
+            rb = {"alg_bytes_per_eval": 288, "hbm": {"achieved": 288 * Ne / (me * 1e-3) / 1e9, "peak": hpk, "unit": "GB/s",
+                                                     "frac": 288 * Ne / (me * 1e-3) / 1e9 / hpk}, "ops_source": ops_src}
+            if ops_db and "eij" in ops_db:
+                sl = ops_db["eij"]["dfma"] + ops_db["eij"]["dmul"] + ops_db["eij"]["dadd"]
+                rb.update({"bound": "fp64", "fp64_slots_per_eval": sl, "achieved": 2.0 * sl * Ne / (me * 1e-3) / 1e12, "peak": fpk,
+                           "unit": "TFLOP/s", "frac": 2.0 * sl * Ne / (me * 1e-3) / 1e12 / fpk, "kernel": "eij_kernel<4> (thread per node)"})
+            ent["roofline"] = rb
+            extra["eij"] = ent
             del st, ugd, eo
         except Exception as ex:   # noqa
             extra["eij"] = {"error": str(ex)[:200]}
@@ -506,15 +739,11 @@ def main():
 
     if rank == 0:
         line = {"metric": "fabric node-updates/s", "value": value, "unit": "node-updates/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "L": L, "nlm_len": n, "nodes_per_gpu": N, "terms": "+".join(terms), "scheme": scheme,
-                           "dt": DT, "l2": "inputs exceed L2 (state %.0f MB per GPU vs 126 MB L2); no flush needed" % (N * n * 16 / 1e6),
-                           "sharding": "contiguous node ranges, no collective while stepping"},
-                "e2e": {"value": e2e_val, "unit": "node-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "sfb_step_arr (host pointers, pinned buffers, chunked H2D|kernel|D2H pipeline)", "host_affinity": numa},
-                "gpu_launches": lps * args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "finite": finite, "other_configs": extra}
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_dict(cfg, n, N, world, args.scaling, total),
+                "e2e": e2e, "gpu_launches": r["launches"] * args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "finite": r["finite"], "parity_spot_max_rel": r["spot"], "parity_spot": "256 nodes of the timed state vs oracle_c replaying %s"
+                % r["spot_steps"], "other_configs": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
