@@ -261,7 +261,8 @@ def roofline_block(sf, key, L, terms, scheme, eij, n, ms_step, N_local, fpk, fsr
         roof = {"bound": "fp64", "achieved": ach_tf, "peak": fpk, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fsrc}
     else:
         roof = {"bound": "hbm", "achieved": ach_gb, "peak": hpk, "unit": "GB/s", "frac": hbm_frac, "peak_source": hsrc}
-    roof.update({"traffic": (traffic_db or {}).get(key),
+    tpn = (traffic_db or {}).get(key)
+    roof.update({"traffic": tpn * N_local if tpn else None, "traffic_bytes_per_node_step": tpn,
                  "kernel": "fused step kernel, L=%d, %s, %s (registry variant %s: %d role(s), %d-node tiles)"
                            % (L, "+".join(terms), scheme, "100/0" if nst > 1 else "0", info["roles"], info["tile"]),
                  "fp64_slots_per_node_step": slots, "fp64_slots_codegen_per_node_step": nominal,
@@ -720,7 +721,8 @@ def main():
                                                      "frac": 288 * Ne / (me * 1e-3) / 1e9 / hpk}, "ops_source": ops_src}
             if ops_db and "eij" in ops_db:
                 sl = ops_db["eij"]["dfma"] + ops_db["eij"]["dmul"] + ops_db["eij"]["dadd"]
-                rb.update({"bound": "fp64", "fp64_slots_per_eval": sl, "achieved": 2.0 * sl * Ne / (me * 1e-3) / 1e12, "peak": fpk,
+                tpe = (traffic_db or {}).get("eij")
+                rb.update({"traffic": tpe * Ne if tpe else None, "bound": "fp64", "fp64_slots_per_eval": sl, "achieved": 2.0 * sl * Ne / (me * 1e-3) / 1e12, "peak": fpk,
                            "unit": "TFLOP/s", "frac": 2.0 * sl * Ne / (me * 1e-3) / 1e12 / fpk, "kernel": "eij_kernel<4> (thread per node)"})
             ent["roofline"] = rb
             extra["eij"] = ent

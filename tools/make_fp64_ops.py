@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import stamp
 
 NODES = {"cfg2": 1_000_000, "euler_L8_lrot": 1_000_000, "cfg5_step": 1_000_000, "cfg3": 1_000_000, "cfg4": 300_000,
-         "cfg2_rnlm": 1_000_000, "euler_L8_lrot_rnlm": 1_000_000, "eij": 4_000_000}
+         "cfg2_rnlm": 1_000_000, "euler_L8_lrot_rnlm": 1_000_000, "eij": 2_000_000}
 
 
 def parse(path):
@@ -43,5 +43,16 @@ if __name__ == "__main__":
                     "pipe_fp64_pct": m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                     "warp_inst_executed": m.get("smsp__inst_executed.sum"), "warp_inst_fp64": m.get("sm__inst_executed_pipe_fp64.sum"),
                     "ncu_duration_us": m.get("gpu__time_duration.sum")}
+    traffic = {"_comment": "DRAM bytes per node-step: (dram__bytes_read.sum + dram__bytes_write.sum) of one launch / nodes of that launch (ncu, same captures as fp64_ops.json); bench.py scales it to its own launch size", "_stamp": out["_stamp"]}
+    for f in sorted(glob.glob(os.path.join(src, "ops_*.csv"))):
+        key = os.path.basename(f)[4:-4]
+        try:
+            m = parse(f)
+            nn = NODES.get(key, 1_000_000)
+            traffic[key] = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / nn          # bytes per node (per evaluation for eij)
+            traffic[key + "_read_write_nodes"] = [int(m["dram__bytes_read.sum"]), int(m["dram__bytes_write.sum"]), nn]
+        except Exception:
+            pass
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     json.dump(out, open(os.path.join(ROOT, "profiles", "fp64_ops.json"), "w"), indent=1)
     print("wrote profiles/fp64_ops.json", sorted(k for k in out if not k.startswith("_")), "stamp", out["_stamp"])
