@@ -155,11 +155,23 @@ def test_taylor_fallback_and_status():
     e = np.tile(np.eye(3)[None], (x.shape[0], 1, 1))
     E, st = sf.Eij_tranisotropic_arr(x, e[:, 0], e[:, 1], e[:, 2], GRAIN, ALPHA, 1, return_status=True)
     nfb = 0
+    conds = []
     for p in range(x.shape[0]):
         ref, rst = orc.Eij_tranisotropic(x[p], e[p, 0], e[p, 1], e[p, 2], GRAIN, ALPHA, 1, return_status=True)
         assert (st[p] & 3) == (1 if rst == 1 else (3 if rst == 2 else 0))
-        if rst <= 1:
-            assert np.abs(E[p] - ref).max() <= 1e-7 * np.abs(ref).max()
+        if rst == 0:
+            assert np.abs(E[p] - ref).max() <= 1e-9 * np.abs(ref).max()
+        elif rst == 1:
+            # The fallback solves (F^T F + 1e-6 I) x = F^T b with the partially factorised F: forming the normal equations
+            # squares the condition number, so two correct FP64 evaluations (LAPACK's blocked dposv here, the kernel's unrolled
+            # Cholesky there) legitimately differ by ~ eps * cond(F^T F + 1e-6 I).  The bound below is that figure with a
+            # factor 100 of slack -- measured conditions are 1e5..1e8, i.e. 1e-9..1e-6 relative -- instead of a blanket 1e-7.
+            P = orc.taylor_P(x[p], GRAIN, 1)
+            c, _, info = orc._dposv(np.array(P, order="F"), np.zeros((6, 1), order="F"), lower=1)
+            Pf = np.array(c)
+            cond = np.linalg.cond(Pf.T @ Pf + orc.TIKHONOV_F * np.eye(6))
+            conds.append(cond)
+            assert info != 0 and np.abs(E[p] - ref).max() <= 100 * 2.2e-16 * cond * np.abs(ref).max(), (cond, np.abs(E[p] / ref - 1).max())
         nfb += rst == 1
     assert nfb > 0, "test did not exercise the fallback branch"
     with pytest.raises(sf.SpecfabB200Error):
