@@ -652,6 +652,20 @@ def main():
             except Exception as ex:   # noqa
                 extra["cfg%d_1e7" % c] = {"error": str(ex)[:200]}
 
+    # config 5 the way an FE coupler drives it (state resident, forcing in, Eij + frame out), at every world size (weak: 1.25e6 per GPU)
+    if not args.no_extra:
+        try:
+            barrier()
+            secc, hc, dc_, okc = time_coupler(sf, torch, 1_250_000, SEED + rank, 5, 2)
+            barrier()
+            secc = max_over_ranks(secc)
+            extra["cfg5_coupler_e2e"] = {"value": 1_250_000 * world / secc, "unit": "node-updates/s", "h2d_bytes_per_step": hc, "d2h_bytes_per_step": dc_,
+                                         "nodes_per_gpu": 1_250_000, "scaling": "weak", "finite": okc,
+                                         "what": "state resident in HBM; per step ugrad + tau in (144 B/node, pinned), Eij + eigenframe + "
+                                                 "eigenvalues out (144 B/node); sfb_step_arr_dev + sfb_Eij_eigenframe_arr_dev on one stream"}
+        except Exception as ex:   # noqa
+            extra["cfg5_coupler_e2e"] = {"error": str(ex)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_extra:
         # config 4 (L = 20) and the other weak-scaling shapes
@@ -686,15 +700,6 @@ def main():
             extra["rnlm"] = rr
         except Exception as ex:   # noqa
             extra["rnlm"] = {"error": str(ex)[:200]}
-        # config 5 the way an FE coupler drives it (state resident, forcing in, Eij + frame out)
-        try:
-            secc, hc, dc_, okc = time_coupler(sf, torch, 1_250_000, SEED, 5, 2)
-            extra["cfg5_coupler_e2e"] = {"value": 1_250_000 / secc, "unit": "node-updates/s", "h2d_bytes_per_step": hc, "d2h_bytes_per_step": dc_,
-                                         "nodes": 1_250_000, "finite": okc,
-                                         "what": "state resident in HBM; per step ugrad + tau in (144 B/node, pinned), Eij + eigenframe + "
-                                                 "eigenvalues out (144 B/node); sfb_step_arr_dev + sfb_Eij_eigenframe_arr_dev on one stream"}
-        except Exception as ex:   # noqa
-            extra["cfg5_coupler_e2e"] = {"error": str(ex)[:200]}
         # stand-alone Eij evals/s (a2 -> eigenframe -> 6 Sachs/Taylor factors per node)
         try:
             lm, n8 = sf.init(8)

@@ -172,7 +172,8 @@ def generate(Ls):
                     meta["dfma_node_full"] = 2 * meta["dfma_node"]
                     split = "split" in cmode.split("+")
                     meta["split"] = int(split)
-                    cu = ('#define SFB_SPLIT %d\n' % int(split)) + ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
+                    npl = max([int(x[3:]) for x in cmode.split("+") if x.startswith("npl")] + [1])
+                    cu = ('#define SFB_NPL %d\n' % npl) + ('#define SFB_SPLIT %d\n' % int(split)) + ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
                           '#define SFB_NAME sfb_launch_step_%s\n#define SFB_WTAB_INC "gen/wtab_L%d_%s.inc"\n'
                           '#include "sfb_step_wloop.cuh"\n' % (L, dd, TN, MINB, tag, L, "ddrx" if dd else "lrot"))
                     path = os.path.join(GEN, "step_%s.cu" % tag)
