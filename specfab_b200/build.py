@@ -66,9 +66,15 @@ EXTRA = {
 EXP = {
     # windowed loop kernel: (variant, -6, one-warp tiles per CTA, register cap)
     (8, 1): [(60, -6, 1, 168, "", False), (61, -6, 1, 255, "", False), (62, -6, 1, 200, "", False), (63, -6, 1, 232, "", False),
-             (70, -6, 1, 168, "+split", False), (71, -6, 1, 128, "+split", False), (72, -6, 1, 144, "+split", False), (73, -6, 1, 200, "+split", False)],
-    (8, 0): [(60, -6, 1, 168, "", False), (61, -6, 1, 128, "", False), (70, -6, 1, 128, "+split", False), (71, -6, 1, 96, "+split", False)],
-    (12, 1): [(70, -6, 1, 168, "+split", False), (71, -6, 1, 200, "+split", False)],
+             (70, -6, 1, 168, "+split", False), (71, -6, 1, 128, "+split", False), (72, -6, 1, 144, "+split", False), (73, -6, 1, 200, "+split", False),
+             (80, -6, 1, 255, "+rowgen", False), (81, -6, 1, 200, "+rowgen", False)],
+    (8, 0): [(60, -6, 1, 168, "", False), (61, -6, 1, 128, "", False), (70, -6, 1, 128, "+split", False), (71, -6, 1, 96, "+split", False),
+             (80, -6, 1, 128, "+rowgen", False)],
+    (12, 1): [(70, -6, 1, 168, "+split", False), (71, -6, 1, 200, "+split", False),
+              (80, -6, 1, 255, "+rowgen", False), (81, -6, 1, 200, "+rowgen", False), (82, -6, 1, 168, "+rowgen", False)],
+    (12, 0): [(80, -6, 1, 128, "+rowgen", False), (81, -6, 1, 96, "+rowgen", False)],
+    # round 2, measured again on the current kernels and dropped (profiles/r02_cbank.txt): "cbank" constants (LDCU.128 pairs instead
+    # of UMOV immediates) for the L = 8 defaults: RK4 LROT 0.56 -> 0.74 ms, Euler 0.26 -> 0.33 ms, DDRX two-lane 0.706 -> 0.708-0.73 ms
     # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
@@ -164,8 +170,10 @@ def generate(Ls):
                 gd = max([int(x[1:]) for x in parts[1:] if x.startswith("g")] + [0])
                 if R == -6:      # windowed loop kernel (one lane per node, register window, constant-cache table); TN field = one-warp tiles per CTA, MINB field = register cap
                     from specfab_b200.codegen import emit_wloop
-                    wtab, wmeta = emit_wloop.emit(L, dd)
-                    _write_if_changed(os.path.join(GEN, "wtab_L%d_%s.inc" % (L, "ddrx" if dd else "lrot")), wtab)
+                    rowgen = "rowgen" in cmode.split("+")
+                    wtab, wmeta = (emit_wloop.emit_rows if rowgen else emit_wloop.emit)(L, dd)
+                    wname = "wtab%s_L%d_%s.inc" % ("r" if rowgen else "", L, "ddrx" if dd else "lrot")
+                    _write_if_changed(os.path.join(GEN, wname), wtab)
                     meta = dict(L=L, ddrx=dd, R=1, TN=32, reduced=1, wloop=1, WPC=TN,
                                 dfma_node=sum(p.dfma for p in emit_step.plan(L, dd)[1]),
                                 dfma_executed=wmeta["dfma_padded"] + 8 * emit_step.nrow_phys(L) // 2, nconst=wmeta["nconst"])
@@ -173,9 +181,9 @@ def generate(Ls):
                     split = "split" in cmode.split("+")
                     meta["split"] = int(split)
                     npl = max([int(x[3:]) for x in cmode.split("+") if x.startswith("npl")] + [1])
-                    cu = ('#define SFB_NPL %d\n' % npl) + ('#define SFB_SPLIT %d\n' % int(split)) + ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
-                          '#define SFB_NAME sfb_launch_step_%s\n#define SFB_WTAB_INC "gen/wtab_L%d_%s.inc"\n'
-                          '#include "sfb_step_wloop.cuh"\n' % (L, dd, TN, MINB, tag, L, "ddrx" if dd else "lrot"))
+                    cu = ('#define SFB_ROWGEN %d\n' % int(rowgen)) + ('#define SFB_NPL %d\n' % npl) + ('#define SFB_SPLIT %d\n' % int(split)) + ('#define SFB_L %d\n#define SFB_DDRX %d\n#define SFB_WPC %d\n#define SFB_MAXREG %d\n'
+                          '#define SFB_NAME sfb_launch_step_%s\n#define SFB_WTAB_INC "gen/%s"\n'
+                          '#include "sfb_step_wloop.cuh"\n' % (L, dd, TN, MINB, tag, wname))
                     path = os.path.join(GEN, "step_%s.cu" % tag)
                     _write_if_changed(path, cu)
                     units.append(path)
@@ -292,8 +300,9 @@ def _deps_hash(src):
         if os.path.exists(os.path.join(GEN, "apply_%s.inc" % tag)):
             files.append(os.path.join(GEN, "apply_%s.inc" % tag))
         base = tag.split("_v")[0]
-        if os.path.exists(os.path.join(GEN, "wtab_%s.inc" % base)):
-            files.append(os.path.join(GEN, "wtab_%s.inc" % base))
+        for wt in ("wtab_%s.inc" % base, "wtabr_%s.inc" % base):
+            if os.path.exists(os.path.join(GEN, wt)):
+                files.append(os.path.join(GEN, wt))
         if os.path.exists(os.path.join(GEN, "apply_%s_full.inc" % tag)):
             files.append(os.path.join(GEN, "apply_%s_full.inc" % tag))
     else:
