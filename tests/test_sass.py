@@ -66,6 +66,28 @@ def test_windowed_loop_reads_its_table_through_the_uniform_datapath(tmp_path, sp
     assert meta["dfma_padded"] == 5260 and meta["dfma_useful"] == 4316 and meta["nconst"] == 1605
 
 
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not found")
+def test_row_generic_form_has_one_small_body_for_every_L(tmp_path):
+    """SFB_ROWGEN at L = 12: the operator loop is ONE row (79 table entries through LDCU, ~240 DFMA) whatever L is."""
+    sys.path.insert(0, ROOT)
+    from specfab_b200.codegen import emit_wloop
+    tab, meta = emit_wloop.emit_rows(12, 1)
+    assert meta["stride"] == 79 and meta["nconst"] == 79 * 49 and meta["dfma_useful"] == 9374
+    (tmp_path / "wtab.inc").write_text(tab)
+    cu = tmp_path / "w.cu"
+    cu.write_text('#define SFB_ROWGEN 1\n#define SFB_L 12\n#define SFB_DDRX 1\n#define SFB_WPC 1\n#define SFB_MAXREG 255\n'
+                  '#define SFB_NAME sfb_launch_step_test\n#define SFB_WTAB_INC "%s"\n#include "sfb_step_wloop.cuh"\n' % str(tmp_path / "wtab.inc"))
+    cubin = str(tmp_path / "w.cubin")
+    p = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+                        "-cubin", "-o", cubin, str(cu)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    sass = subprocess.run(["cuobjdump", "-sass", cubin], capture_output=True, text=True).stdout
+    bodies = [(n, c) for n, c in loops_of(sass, "step_kernel_wrE") if c["DFMA"] >= 200]
+    assert bodies, "no operator loop found"
+    n, c = min(bodies, key=lambda b: b[0])
+    assert n < 1200 and 230 <= c["DFMA"] <= 300 and c["LDCU"] >= 79 and c["LDC"] <= 12, (n, dict(c))
+
+
 def test_default_step_kernels_use_tma_bulk_copies_and_mbarriers():
     obj = os.path.join(ROOT, "specfab_b200", "_build", "step_L8_lrot.o")
     if not os.path.exists(obj):
