@@ -626,7 +626,7 @@ def eig(nlm):
 
 def Eij_orthotropic(nlm_1, nlm_2, nlm_3, e1, e2, e3, Eij_grain, alpha, n_grain):
     """reference: src/specfabpy.f90:436-446 -> Eij[6]"""
-    one = lambda v: np.asarray(v)[None, :]
+    one = lambda v: None if v is None else np.asarray(v)[None, :]
     return np.ascontiguousarray(Eij_orthotropic_arr(one(nlm_1), one(nlm_2), one(nlm_3), one(e1), one(e2), one(e3), Eij_grain, alpha, n_grain)[0])
 
 

@@ -265,6 +265,8 @@ def test_Eij_orthotropic_parity(third):
     assert np.abs(E / ref - 1).max() < 1e-11
     # scalar entry point
     assert np.array_equal(sf.Eij_orthotropic(q1[5], q2[5], q3r[5], e1[5], e2[5], e3[5], OLIVINE, 0.0, 1), E[5])
+    if third == "null":      # nlm_3 = None is accepted by the scalar form too
+        assert np.array_equal(sf.Eij_orthotropic(q1[5], q2[5], None, e1[5], e2[5], e3[5], OLIVINE, 0.0, 1), E[5])
 
 
 def test_Eij_orthotropic_pins_and_errors():
