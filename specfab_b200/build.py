@@ -75,6 +75,8 @@ EXP = {
     (12, 0): [(80, -6, 1, 128, "+rowgen", False), (81, -6, 1, 96, "+rowgen", False)],
     # round 2, measured again on the current kernels and dropped (profiles/r02_cbank.txt): "cbank" constants (LDCU.128 pairs instead
     # of UMOV immediates) for the L = 8 defaults: RK4 LROT 0.56 -> 0.74 ms, Euler 0.26 -> 0.33 ms, DDRX two-lane 0.706 -> 0.708-0.73 ms
+    # 14 / 16 warps per SM for the L = 8 RK4 default (128 registers instead of 168: 450-650 bytes of spills, static FP64 share 0.71 -> 0.61):
+    # 0.559 -> 0.82-0.89 ms, reduced-form I/O 0.451 -> 0.60-0.66 ms (profiles/r02_occupancy.txt)
     # tried and dropped in this session (profiles/r01_variants_sweep_a32.txt): "+ch4" loop kernels (L = 12, 20: 25-50 % slower),
     # one-lane straight-line DDRX kernels with 2-8 tiles per CTA at L = 8 (1.12 ms vs 0.73 ms for the two-lane form),
     # lock-stepped tiles "+ls" (no gain over free-running tiles that start together), two-lane L = 8 DDRX kernel with 96-node
