@@ -140,6 +140,7 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (!RIO && warp == 1) prefetch_mirror_rows(P.nlm_in, P.ld_in, node0, nvalid, kL, lane, 32);
     if (warp == 0) {
         const uint32_t bytes = (uint32_t)nvalid * 16u;
         if (lane == 0)
@@ -165,6 +166,17 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
             if (task == 1) prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
 #endif
         }
+    }
+    // ---- this lane's component of the mirror rows (m < 0), for the real-ODF test: issued now that the forcing preparation has
+    // released its registers, all loads in flight together (L2 hits after the prefetch above), consumed after the wait and <D>
+    constexpr int kNNegR = kNCoef - kNRowR;
+    double vneg[kNNegR > 0 ? kNNegR : 1];
+    if (!RIO && valid) {
+        const double* gneg = reinterpret_cast<const double*>(P.nlm_in + node0 + nl) + comp;
+#pragma unroll
+        for (int l = 2; l <= kL; l += 2)
+#pragma unroll
+            for (int m = 1; m <= l; ++m) vneg[(l / 2) * (l / 2 - 1) + m - 1] = gneg[2 * ((long long)(hrow(l) - m) * P.ld_in)];
     }
     {
         uint32_t done = 0;
@@ -192,21 +204,16 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
     // ---- real-ODF symmetry of the input to round-off, each lane tests its own component of the mirror rows
     bool bad = false;
     if (!RIO && valid) {
-        const double* gneg = reinterpret_cast<const double*>(P.nlm_in + node0 + nl) + comp;
         const double tol = kSymTol * fabs(reinterpret_cast<const double*>(bufs)[2 * nl]);
 #pragma unroll
         for (int l = 0; l <= kL; l += 2) {
             if (comp) bad |= !(fabs(dbuf[2 * pslot(l, 0) * kTNR]) <= tol);
-            double vl[kL > 0 ? kL : 1];
-#pragma unroll
-            for (int m = 1; m <= kL; ++m)
-                if (m <= l) vl[m - 1] = gneg[2 * ((long long)(hrow(l) - m) * P.ld_in)];
 #pragma unroll
             for (int m = 1; m <= kL; ++m)
                 if (m <= l) {
                     const double vp = dbuf[2 * pslot(l, m) * kTNR];
                     const double ex = (((m & 1) != 0) == (comp != 0)) ? vp : -vp;     // re: (-1)^m vp ; im: -(-1)^m vp
-                    bad |= !(fabs(vl[m - 1] - ex) <= tol);
+                    bad |= !(fabs(vneg[(l / 2) * (l / 2 - 1) + m - 1] - ex) <= tol);
                 }
         }
     }

@@ -208,6 +208,8 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
     constexpr int kNNeg = kNCoef - kNRowR;
     constexpr bool kBatchAll = kNNeg <= 42 && !SFB_DDRX && !RIO;   // LROT kernels up to L = 12: every mirror row in registers
                                                          // (the DDRX preparation needs the registers: per-degree batches there)
+    if (!RIO && !kBatchAll && warp == (kR > 1 ? kR - 1 : 0))
+        prefetch_mirror_rows(P.nlm_in, P.ld_in, node0, nvalid, kL, t, 32);        // tested after the wait: have them in L2 by then
     double2 vneg[kBatchAll ? (kNNeg > 0 ? kNNeg : 1) : 1];
     const double2* gneg = P.nlm_in + node0 + (valid ? t : 0);
     if (!RIO && kBatchAll && warp == 0) {

@@ -63,3 +63,17 @@ __device__ __forceinline__ int cat_mirror(int k) { return k == 0 ? 0 : (k < 6 ? 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+
+// L2 prefetch of the mirror rows (m < 0) of a tile, issued next to the bulk copies of the rows m >= 0: the real-ODF test reads them
+// from global memory AFTER the tile has landed (the registers are needed by the forcing preparation in between), and would
+// otherwise wait for DRAM at that point.  Lanes lane0, lane0 + nlanes, ... each take full-form rows j = hrow(l) + m with m < 0.
+__device__ __forceinline__ void prefetch_mirror_rows(const double2* nlm_in, long long ld, long long node0, int nvalid, int L, int lane0, int nlanes) {
+    const int ncoef = (L + 1) * (L + 2) / 2;
+    const unsigned bytes = (unsigned)nvalid * 16u;
+    for (int j = lane0; j < ncoef; j += nlanes) {
+        int l = 0;
+        while ((l + 2) * (l + 1) / 2 <= j) l += 2;           // first row of degree l + 2 is (l + 2)(l + 1)/2
+        const int m = j - l * (l + 1) / 2;
+        if (m < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nlm_in + (long long)j * ld + node0), "r"(bytes) : "memory");
+    }
+}
