@@ -45,10 +45,18 @@ __device__ __forceinline__ void load_tau(const ForcSrc& S, double T[3][3]) {
 // TNS: node stride of the forcing / scalar arrays; WITHB: also fill the mirrored block of lane set B
 // (the one-lane reduced kernel, sfb_step_kernel_r.cuh, needs set A only)
 template <int TNS = kTN, bool WITHB = true>
-__device__ void prep_lrot(const SfbStepParams& P, const ForcSrc& S, long long node, int t, double2* forc, double* scal) {
+__device__ void prep_lrot(const SfbStepParams& P, const ForcSrc& S, long long node, int t, double2* forc, double* scal,
+                          const double* upre = nullptr) {      // upre: the node's ugrad (element (i,k) at i + 3k) when the caller loaded it early
     constexpr int kTN = TNS;                   // shadows the tile constant inside this function
     double D[3][3], W[3][3];
-    load_sym_skew(S, D, W);
+    if (upre) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { D[i][j] = (upre[i + 3 * j] + upre[j + 3 * i]) / 2; W[i][j] = (upre[i + 3 * j] - upre[j + 3 * i]) / 2; }
+    } else {
+        load_sym_skew(S, D, W);
+    }
     double2* fA = forc + t;                    // lane set A block: entry e at fA[e*kTN]
     double2* fB = forc + kNF * kTN + t;        // lane set B block
     // ---- M_LROT weights, src/dynamics.f90:71-76

@@ -179,6 +179,13 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
     if (kCW > 1 && node0 >= P.N) return;              // exited warps do not count at later CTA barriers
     const int nvalid = (int)min((long long)kTNR, P.N - node0);
     const bool valid = t < nvalid;
+    // the node's velocity gradient, needed first thing by the forcing preparation: requested before the tile is staged so that
+    // its DRAM latency runs under the mbarrier set-up and the bulk-copy issue loop
+    double upre[9];
+    if (valid && warp == 0) {
+#pragma unroll
+        for (int p = 0; p < 9; ++p) upre[p] = P.ugrad[(long long)p * P.ld_u + node0 + t];
+    }
 
     // ---- stage the rows m >= 0 of the tile (one bulk copy per row) into buffer 0
     const uint32_t mb = smem_u32(mbar);
@@ -221,7 +228,7 @@ __device__ __forceinline__ void step_tile_r(const SfbStepParams& P, unsigned cha
     // ---- meanwhile: per-node forcing (lane set A only); with several roles the tasks go to different warps
     if (valid) {
         const ForcSrc S = global_src(P, node0 + t);
-        if (warp == 0) prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal);
+        if (warp == 0) prep_lrot<kTNR, false>(P, S, node0 + t, t, forc, scal, upre);
 #if SFB_DDRX
         if (warp == (kR > 1 ? 1 : 0)) prep_ddrx_g<kTNR, false>(P, S, node0 + t, t, forc, scal);
 #endif
